@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the correlation + flow_warp hot path (BASELINE.json).
+
+Workload (config.workload): BASELINE.json configs[1], "PWC-Lite kitti_base training step,
+synthetic 256x832 pairs, B=8, 1 B200" restricted to the path this repo owns: every Correlation
+and flow_warp call of one training iteration, forward and backward (unsamflow_b200/hotpath.py:
+10 corr fwd + 10 corr bwd + 16 warp fwd + 16 warp bwd), on seeded synthetic tensors.
+
+  value      pairs/s with all inputs resident in HBM; a step = CUDA graph A -> the dominant op launched
+             eagerly between two CUDA events -> CUDA graph B.  L2 is flushed between steps (outside
+             the per-step event pair).  Device time from CUDA events, max over ranks.
+  e2e        same step through the public tensor API with HOST inputs: H2D of every input from pinned
+             memory and D2H of the step's results are inside the timed region.
+  roofline   the dominant op's kernel: algorithmic bytes per launch / mean launch duration (events
+             inside the timed region) against MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference
+             the reference's CPU path (oracle/torch_port.py: the same ATen calls the reference
+             makes) on the host cores, on a bounded sample (1 pair per step).
+
+Launch: python bench.py [--gpus N --steps K --warmup W]; for N > 1 under torchrun (one rank per GPU,
+weak scaling: every rank runs its own B=8 batch, no data-path collective).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "corr+warp fwd+bwd hot path of a PWC-Lite kitti_base training step: pairs/s (GB/s vs HBM peak in roofline)"
+UNIT = "pairs/s"
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12  # CUDA-core FFMA peak at max SM clock
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--height", type=int, default=256)
+    ap.add_argument("--width", type=int, default=832)
+    ap.add_argument("--flow-sigma", type=float, default=3.0)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--cpu-reps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--op-table", default="", help="write the per-op timing table (JSON) here")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference CPU path (the ONLY place bench.py touches oracle/): cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_step(B, H, W, flow_sigma, seed=42):
+    """Build closures that run the same op schedule as HotPathStep through the torch port on CPU."""
+    from oracle import torch_port
+    from unsamflow_b200 import hotpath
+    gen = torch.Generator().manual_seed(seed)
+    levels, scales = hotpath.pyramid_shapes(H, W), hotpath.loss_shapes(H, W)
+    data = []
+    for lvl, (C, h, w) in enumerate(levels):
+        f1, f2 = torch.randn(B, C, h, w, generator=gen), torch.randn(B, C, h, w, generator=gen)
+        for _ in range(2):  # two directions
+            fl = flow_sigma * torch.randn(B, 2, h, w, generator=gen)
+            go = torch.randn(B, 81, h, w, generator=gen)
+            data.append(("model", lvl, f1, f2, fl, go))
+            f1, f2 = f2, f1
+    for (C, h, w) in scales:
+        for _ in range(2):
+            im = torch.rand(B, C, h, w, generator=gen)
+            fl = flow_sigma * torch.randn(B, 2, h, w, generator=gen)
+            go = torch.randn(B, C, h, w, generator=gen)
+            data.append(("loss", 0, im, None, fl, go))
+
+    def step():
+        for kind, lvl, a, b, fl, go in data:
+            if kind == "model":
+                x1 = a.clone().requires_grad_(True)
+                x2 = b.clone().requires_grad_(True)
+                f = fl.clone().requires_grad_(True)
+                x2w = torch_port.flow_warp(x2, f) if lvl > 0 else x2
+                torch_port.cost_volume(x1, x2w).backward(go)
+            else:
+                f = fl.clone().requires_grad_(True)
+                torch_port.flow_warp(a, f, pad="border").backward(go)
+    return step
+
+
+def time_cpu_reference(args, steps, warmup, sample_pairs=1, budget_s=120.0):
+    """Times `steps` CPU steps (stops early once budget_s of timed work is spent; the JSON says so)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_reference_step(sample_pairs, args.height, args.width, args.flow_sigma)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    done = 0
+    while done < steps and (done == 0 or time.perf_counter() - t0 < budget_s):
+        step()
+        done += 1
+    steps = done
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": sample_pairs / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample_pairs} pair(s) per step of the same op schedule ({steps} timed steps, "
+                      f"{warmup} warm-up), oracle/torch_port.py on torch {torch.__version__} CPU",
+            "ms_per_step": dt * 1e3, "steps": steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    warmup = max(1, min(args.warmup, 2))
+    cb = time_cpu_reference(args, max(1, args.steps), warmup)
+    steps = cb["steps"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, extra={"note": "CPU reference path; step bounded to 1 pair; "
+                                                        f"{steps} of --steps {args.steps} run inside a 120 s budget"}),
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, extra=None):
+    cfg = {"workload": f"PWC-Lite kitti_base training-step hot path (corr+flow_warp fwd+bwd), synthetic "
+                       f"{args.height}x{args.width} pairs, B={args.batch} per GPU",
+           "batch_per_gpu": args.batch, "height": args.height, "width": args.width, "max_displacement": 4,
+           "flow_sigma_px": args.flow_sigma, "parallelism": f"dp{args.gpus} (batch replicas, no data-path collective)"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+
+    def __init__(self, index, period=0.01):
+        super().__init__(daemon=True)
+        self.period, self.samples, self.stop_flag, self.h, self.ok = period, [], False, None, False
+        self.marks = []
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            try:
+                mhz = self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+                try:
+                    rs = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    rs = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, rs))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def summary(self, t0, t1):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvml unavailable: " + self.err}
+        win = [s for s in self.samples if t0 <= s[0] <= t1]
+        note = "sampled inside the timed region"
+        if len(win) < 3:
+            win, note = self.samples, "timed region too short for 3 samples: includes warm-up"
+        mask = 0
+        for s in win:
+            mask |= s[2]
+        reasons = sorted({name for bit, name in self.REASONS.items() if mask & bit})
+        return {"sm_mhz": statistics.median([s[1] for s in win]) if win else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(win), "note": note}
+
+
+# ------------------------------------------------------------------------------------------------
+# ours
+# ------------------------------------------------------------------------------------------------
+def capture(fn):
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return g
+
+
+def per_launch_bytes(op):
+    B, C, H, W = op.shape
+    if op.kind == "corr_bwd":  # each of the two launches reads gO + one feature map and writes one gradient
+        return (81 + 2 * C) * 4 * B * H * W
+    return op.bytes // max(1, op.launches)
+
+
+def run_ours(args):
+    from unsamflow_b200 import ops
+    from unsamflow_b200.hotpath import HotPathStep
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; unsamflow_b200 has no CPU path (use --impl reference)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step = HotPathStep(args.batch, args.height, args.width, device=f"cuda:{local}", flow_sigma=args.flow_sigma)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=step.device)  # > 126 MB L2
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    # ---- per-op table (also picks the dominant op) ------------------------------------------------
+    for op in step.ops:
+        op.fn()
+    torch.cuda.synchronize()
+    table = []
+    for op in step.ops:
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            a, b = ev(), ev()
+            a.record(); op.fn(); b.record()
+            b.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        us = statistics.median(ts)
+        table.append({"op": op.name, "kind": op.kind, "shape": list(op.shape), "us_cold_l2": round(us, 2),
+                      "launches": op.launches, "alg_MB": round(op.bytes / 1e6, 3),
+                      "GBps": round(op.bytes / us / 1e3, 1), "TFLOPs": round(op.flops / us / 1e6, 2)})
+    dom_i = max(range(len(step.ops)), key=lambda i: table[i]["us_cold_l2"])
+    dom = step.ops[dom_i]
+    if args.op_table and rank == 0:
+        os.makedirs(os.path.dirname(os.path.abspath(args.op_table)), exist_ok=True)
+        with open(args.op_table, "w") as f:
+            json.dump(table, f, indent=1)
+
+    # ---- graphs: A (before the dominant op), eager dominant op, B (after) ----------------------------
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step.run()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    before, after = step.ops[:dom_i], step.ops[dom_i + 1:]
+    gA = capture(lambda: step.run(before)) if before else None
+    gB = capture(lambda: step.run(after)) if after else None
+    gFull = capture(step.run)
+
+    def one_step(e0=None, e1=None):
+        if gA is not None:
+            gA.replay()
+        if e0 is not None:
+            e0.record()
+        dom.fn()
+        if e1 is not None:
+            e1.record()
+        if gB is not None:
+            gB.replay()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(args.warmup):
+        flush.zero_()
+        one_step()
+    barrier()
+    ops.reset_launch_count()
+    t_wall0 = time.perf_counter()
+    marks = []
+    for _ in range(args.steps):
+        flush.zero_()
+        s0, e0, e1, s1 = ev(), ev(), ev(), ev()
+        s0.record()
+        one_step(e0, e1)
+        s1.record()
+        marks.append((s0, e0, e1, s1))
+    barrier()
+    t_wall1 = time.perf_counter()
+    eager_launches = ops.launch_count()  # launches issued through the ABI outside graph replays
+    total_ms = sum(s0.elapsed_time(s1) for s0, _, _, s1 in marks)
+    dom_ms = sum(e0.elapsed_time(e1) for _, e0, e1, _ in marks) / args.steps
+    clocks = sampler.summary(t_wall0, t_wall1)
+
+    # ---- e2e: host inputs -> H2D -> step -> D2H results, all inside the timed region ---------------
+    host_in = {n: step.t[n].cpu().pin_memory() for n in step.input_names}
+    res_names = step.result_names()
+    host_out = {n: torch.empty_like(step.t[n], device="cpu").pin_memory() for n in res_names}
+    e2e_marks = []
+
+    def e2e_step():
+        for n, h in host_in.items():
+            step.t[n].copy_(h, non_blocking=True)
+        gFull.replay()
+        for n, h in host_out.items():
+            h.copy_(step.t[n], non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    for _ in range(args.e2e_steps):
+        a, b = ev(), ev()
+        a.record(); e2e_step(); b.record()
+        e2e_marks.append((a, b))
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_marks)
+    sampler.stop_flag = True
+
+    stats = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=step.device)
+    if dist is not None:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = stats.tolist()
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        launches = dom.launches
+        alg = per_launch_bytes(dom)
+        dom_us = dom_ms * 1e3 / launches
+        achieved = alg / dom_us / 1e3  # GB/s
+        line = {
+            "metric": METRIC, "value": world * args.batch * args.steps / (total_ms / 1e3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, extra={
+                "l2": "256 MB L2 flush between timed steps (outside the per-step CUDA-event pair); "
+                      "step working set ~1 GB > 126 MB L2",
+                "step": "CUDA graph A + eager dominant op between events + CUDA graph B"}),
+            "hot_path_gbs": world * step.bytes_per_step * args.steps / (total_ms / 1e3) / 1e9,
+            "hot_path_tflops": world * step.flops_per_step * args.steps / (total_ms / 1e3) / 1e12,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": dom.name, "kind": dom.kind, "shape": list(dom.shape),
+                         "launches_per_op": launches, "alg_bytes_per_launch": alg, "us_per_launch": dom_us,
+                         "peak_source": peak_src,
+                         "fp32_tflops": (dom.flops / launches) / dom_us / 1e6 if dom.flops else None,
+                         "fp32_peak_tflops": FP32_PEAK_TFLOPS},
+            "e2e": {"value": world * args.batch * args.e2e_steps / (e2e_ms / 1e3), "unit": UNIT,
+                    "h2d_bytes_per_step": step.input_bytes(),
+                    "d2h_bytes_per_step": sum(h.numel() * h.element_size() for h in host_out.values()),
+                    "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps},
+            "gpu_launches": step.launches_per_step * args.steps,
+            "gpu_launches_note": f"{step.launches_per_step} usf kernels per step ({eager_launches} issued eagerly "
+                                 "through the C ABI in the timed region, the rest replayed from CUDA graphs)",
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = time_cpu_reference(args, steps=args.cpu_reps, warmup=1)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,73 @@
+"""The C-ABI library loads and exports every symbol include/unsamflow_b200.h declares.
+No GPU needed: only argument validation paths are called (they return before any CUDA call)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "unsamflow_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from unsamflow_b200 import build, _lib
+    build.build()
+    return _lib.load()
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(usf_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported(lib):
+    from unsamflow_b200 import _lib
+    names = declared_symbols()
+    assert len(names) == 10
+    assert sorted(_lib.SYMBOLS) == names
+    for n in names:
+        assert getattr(lib, n) is not None
+
+
+def test_abi_version_and_status_strings(lib):
+    assert lib.usf_abi_version() == 1
+    for st in (0, -1, -2, -3, -4, -5):
+        assert lib.usf_status_string(st)
+    assert b"unknown" in lib.usf_status_string(-99)
+
+
+def test_argument_validation_without_a_gpu(lib):
+    buf = (ctypes.c_float * 16)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    BAD_SHAPE, BAD_ARG, WORKSPACE, UNSUPPORTED = -1, -2, -3, -5
+    # null pointers / wrong displacement / unknown flag / unknown dtype
+    assert lib.usf_corr_fwd(None, p, p, 1, 1, 2, 2, 4, 0, 0, 0.0, None) == BAD_ARG
+    assert lib.usf_corr_fwd(p, p, p, 1, 1, 2, 2, 3, 0, 0, 0.0, None) == BAD_ARG
+    assert lib.usf_corr_fwd(p, p, p, 1, 1, 2, 2, 4, 0, 64, 0.0, None) == BAD_ARG
+    assert lib.usf_corr_fwd(p, p, p, 1, 1, 2, 2, 4, 7, 0, 0.0, None) == BAD_ARG
+    assert lib.usf_corr_fwd(p, p, p, 1, 1, 2, 2, 4, 1, 0, 0.0, None) == UNSUPPORTED  # bf16: not yet
+    # shapes: non-positive, and more than 2^31-1 elements
+    assert lib.usf_corr_fwd(p, p, p, 0, 1, 2, 2, 4, 0, 0, 0.0, None) == BAD_SHAPE
+    assert lib.usf_corr_fwd(p, p, p, 64, 512, 1024, 1024, 4, 0, 0, 0.0, None) == BAD_SHAPE
+    assert lib.usf_corr_bwd(p, p, None, p, p, 1, 1, 2, 2, 4, 0, 0, None) == BAD_ARG
+    assert lib.usf_corr_bwd(p, p, p, None, None, 1, 1, 2, 2, 4, 0, 0, None) == 0  # nothing requested
+    # warp: pad mode, H/W >= 2 (the reference divides by size-1), workspace
+    assert lib.usf_warp_fwd(p, p, p, 1, 1, 2, 2, 5, 0, 0, None) == BAD_ARG
+    assert lib.usf_warp_fwd(p, p, p, 1, 1, 1, 2, 0, 0, 0, None) == BAD_SHAPE
+    assert lib.usf_warp_bwd(p, p, p, None, None, 1, 1, 2, 2, 0, 0, 0, None, 0, None) == 0
+    assert lib.usf_warp_bwd(p, p, p, p, p, 1, 1, 2, 2, 0, 0, 0, None, 0, None) == WORKSPACE
+    need = lib.usf_warp_bwd_workspace_bytes(1, 1, 2, 2, 0)
+    assert need > 0
+    assert lib.usf_warp_bwd(p, p, p, p, p, 1, 1, 2, 2, 0, 0, 0, p, need - 1, None) == WORKSPACE
+    assert lib.usf_warp_bwd_workspace_bytes(1, 1, 2, 2, 4) == 0  # atomic mode needs none
+    assert lib.usf_warp_bwd_workspace_bytes(8, 32, 64, 208, 0) == 8 * 64 * 208 * (4 + 64 + 48) + 16
+
+
+def test_launch_counter_is_per_thread_and_resettable(lib):
+    lib.usf_reset_launch_count()
+    assert lib.usf_launch_count() == 0
+    assert lib.usf_last_cuda_error() == 0

@@ -1,0 +1,390 @@
+"""GPU parity: the CUDA path (through the C ABI) against the reference's golden vectors and the
+oracle.  Tolerance for fp32 (BASELINE.json north_star): 1e-5 relative, measured both as rel-L2 and
+as max-abs error normalised by the reference's max-abs.
+
+Nothing here reads /root/reference: fixtures are committed, the oracle is oracle/ (C + torch port).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import max_norm_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def usf():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import unsamflow_b200
+    from unsamflow_b200 import ops
+    unsamflow_b200.ops_mod = ops
+    return unsamflow_b200
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def check(got, want, what, tol=TOL):
+    got = got.detach().cpu().numpy() if isinstance(got, torch.Tensor) else got
+    want = want.detach().cpu().numpy() if isinstance(want, torch.Tensor) else want
+    assert got.shape == want.shape, what
+    assert np.isfinite(got).all(), what
+    e1, e2 = rel_l2(got, want), max_norm_err(got, want)
+    assert e1 <= tol and e2 <= tol, f"{what}: rel_l2={e1:.3e} max_norm={e2:.3e} (tol {tol})"
+
+
+# --------------------------------------------------------------------------------------------
+# golden vectors produced by the unmodified reference
+# --------------------------------------------------------------------------------------------
+def test_corr_matches_reference_golden(usf, corr_golden):
+    ops = usf.ops_mod
+    for name, t in corr_golden.items():
+        x1, x2, go = dev(t["x1"]), dev(t["x2"]), dev(t["gout"])
+        check(ops.corr_fwd(x1, x2), t["out"], f"{name}.out")
+        g1, g2 = ops.corr_bwd(x1, x2, go)
+        check(g1, t["gx1"], f"{name}.gx1")
+        check(g2, t["gx2"], f"{name}.gx2")
+
+
+def test_warp_matches_reference_golden(usf, warp_golden):
+    ops = usf.ops_mod
+    for name, t in warp_golden.items():
+        pad = str(t["pad"])
+        x, fl, go = dev(t["x"]), dev(t["flow"]), dev(t["gout"])
+        check(ops.warp_fwd(x, fl, pad), t["out"], f"{name}.out")
+        for atomic in (False, True):
+            gx, gfl = ops.warp_bwd(x, fl, go, pad, atomic=atomic)
+            check(gx, t["gx"], f"{name}.gx(atomic={atomic})")
+            check(gfl, t["gflow"], f"{name}.gflow(atomic={atomic})")
+
+
+def test_autograd_modules_match_reference_golden(usf, corr_golden, warp_golden):
+    t = corr_golden["c32_tile_edges"]
+    x1, x2 = dev(t["x1"]).requires_grad_(True), dev(t["x2"]).requires_grad_(True)
+    corr = usf.Correlation(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1,
+                           corr_multiply=1)
+    out = corr(x1, x2)
+    check(out, t["out"], "module out")
+    # the caller mutates the output in place (models/pwclite.py:308) before backward
+    out2 = torch.nn.functional.leaky_relu(out, 0.1, inplace=True)
+    go = dev(t["gout"])
+    out2.backward(go)
+    slope = torch.where(dev(t["out"]) > 0, 1.0, 0.1)
+    from oracle import c_oracle
+    g1, g2 = c_oracle.corr_bwd(t["x1"], t["x2"], (go * slope).cpu().numpy())
+    check(x1.grad, g1, "module gx1 through in-place LeakyReLU")
+    check(x2.grad, g2, "module gx2 through in-place LeakyReLU")
+
+    t = warp_golden["border_c32"]
+    x, fl = dev(t["x"]).requires_grad_(True), dev(t["flow"]).requires_grad_(True)
+    y = usf.flow_warp(x, fl)  # positional call like models/pwclite.py:302
+    y.backward(dev(t["gout"]))
+    check(y, t["out"], "flow_warp out")
+    check(x.grad, t["gx"], "flow_warp gx")
+    check(fl.grad, t["gflow"], "flow_warp gflow")
+    # loss-side call: keyword pad, gradient wrt flow only (losses/flow_loss.py:130)
+    t = warp_golden["border_img_wide"]
+    x, fl = dev(t["x"]), dev(t["flow"]).requires_grad_(True)
+    usf.flow_warp(x, fl, pad="border").backward(dev(t["gout"]))
+    check(fl.grad, t["gflow"], "flow_warp gflow only")
+
+
+# --------------------------------------------------------------------------------------------
+# oracle on seeded inputs: every pyramid level of the BASELINE configs, ragged / edge shapes
+# --------------------------------------------------------------------------------------------
+CORR_SHAPES = [
+    # KITTI 256x832 pyramid, B=1 (configs[0]) and the B=8 bench sizes at the two ends
+    (1, 192, 4, 13), (1, 128, 8, 26), (1, 96, 16, 52), (1, 64, 32, 104), (1, 32, 64, 208),
+    (8, 192, 4, 13), (2, 32, 64, 208),
+    # Sintel 384x832 and crops: odd widths, tile remainders
+    (1, 128, 12, 26), (1, 64, 48, 104), (1, 192, 3, 10), (1, 96, 20, 44), (1, 192, 5, 11),
+    # microbench sweep corner: C not a multiple of 8, C tiny, single pixel row/col
+    (1, 196, 9, 33), (2, 3, 17, 70), (1, 1, 8, 32), (1, 40, 1, 5), (1, 33, 7, 1),
+]
+
+
+@pytest.mark.parametrize("shape", CORR_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_corr_vs_oracle(usf, shape):
+    from oracle import c_oracle
+    ops = usf.ops_mod
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(1234 + C + H)
+    x1, x2 = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+    go = torch.randn(B, 81, H, W, generator=g)
+    out = ops.corr_fwd(x1.cuda(), x2.cuda())
+    check(out, c_oracle.corr_fwd(x1.numpy(), x2.numpy()), "out")
+    g1, g2 = ops.corr_bwd(x1.cuda(), x2.cuda(), go.cuda())
+    o1, o2 = c_oracle.corr_bwd(x1.numpy(), x2.numpy(), go.numpy())
+    check(g1, o1, "gx1")
+    check(g2, o2, "gx2")
+
+
+def test_corr_full_size_b8_vs_oracle(usf):
+    """configs[1] largest level at the bench batch size, against the (multi-threaded) C oracle."""
+    from oracle import c_oracle
+    ops = usf.ops_mod
+    shape = (8, 32, 64, 208)
+    g = torch.Generator().manual_seed(7)
+    x1, x2 = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+    go = torch.randn(8, 81, 64, 208, generator=g)
+    check(ops.corr_fwd(x1.cuda(), x2.cuda()), c_oracle.corr_fwd(x1.numpy(), x2.numpy()), "out")
+    g1, g2 = ops.corr_bwd(x1.cuda(), x2.cuda(), go.cuda())
+    o1, o2 = c_oracle.corr_bwd(x1.numpy(), x2.numpy(), go.numpy())
+    check(g1, o1, "gx1")
+    check(g2, o2, "gx2")
+
+
+def test_corr_nullable_grads_and_unaligned_views(usf):
+    from oracle import c_oracle
+    ops = usf.ops_mod
+    g = torch.Generator().manual_seed(3)
+    x1, x2 = torch.randn(2, 16, 12, 24, generator=g), torch.randn(2, 16, 12, 24, generator=g)
+    go = torch.randn(2, 81, 12, 24, generator=g)
+    o1, o2 = c_oracle.corr_bwd(x1.numpy(), x2.numpy(), go.numpy())
+    g1, none = ops.corr_bwd(x1.cuda(), x2.cuda(), go.cuda(), need_gx2=False)
+    assert none is None
+    check(g1, o1, "gx1 only")
+    none, g2 = ops.corr_bwd(x1.cuda(), x2.cuda(), go.cuda(), need_gx1=False)
+    assert none is None
+    check(g2, o2, "gx2 only")
+    # storage offset of 4 bytes -> the 16-byte vector path must not be taken
+    buf = torch.zeros(x1.numel() + 1).cuda()
+    buf[1:] = x1.flatten().cuda()
+    x1u = buf[1:].view_as(x1)
+    assert x1u.data_ptr() % 16 != 0
+    check(ops.corr_fwd(x1u, x2.cuda()), c_oracle.corr_fwd(x1.numpy(), x2.numpy()), "unaligned out")
+    # non-contiguous input (channels-last strides) is made contiguous at the boundary
+    x2cl = x2.cuda().to(memory_format=torch.channels_last)
+    check(ops.corr_fwd(x1.cuda(), x2cl), c_oracle.corr_fwd(x1.numpy(), x2.numpy()), "channels_last out")
+
+
+def test_corr_fused_leaky_relu(usf):
+    ops = usf.ops_mod
+    g = torch.Generator().manual_seed(5)
+    x1, x2 = torch.randn(1, 32, 16, 52, generator=g).cuda(), torch.randn(1, 32, 16, 52, generator=g).cuda()
+    plain = ops.corr_fwd(x1, x2)
+    fused = ops.corr_fwd(x1, x2, leaky_slope=0.1)
+    assert torch.equal(fused, torch.nn.functional.leaky_relu(plain, 0.1))
+
+
+WARP_SHAPES = [
+    # model-side warps (levels 1..4) and loss-side image warps of the KITTI / Sintel configs
+    (1, 128, 8, 26), (1, 96, 16, 52), (1, 64, 32, 104), (2, 32, 64, 208), (1, 3, 256, 832),
+    (1, 3, 48, 104), (1, 2, 64, 208), (1, 196, 5, 11), (1, 1, 2, 2), (2, 17, 9, 31),
+]
+
+
+@pytest.mark.parametrize("pad", ["border", "zeros"])
+@pytest.mark.parametrize("kind", ["gauss", "wild", "integer", "subpixel_edges"])
+@pytest.mark.parametrize("shape", WARP_SHAPES, ids=lambda s: "x".join(map(str, s)))
+def test_warp_vs_oracle(usf, shape, kind, pad):
+    from oracle import c_oracle
+    ops = usf.ops_mod
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(99 + C + H)
+    x, go = torch.randn(shape, generator=g), torch.randn(shape, generator=g)
+    if kind == "gauss":
+        fl = 3.0 * torch.randn(B, 2, H, W, generator=g)
+    elif kind == "wild":
+        fl = torch.randn(B, 2, H, W, generator=g) * torch.tensor([W / 4.0, H / 4.0]).view(1, 2, 1, 1)
+    elif kind == "integer":
+        fl = torch.randint(-3, 4, (B, 2, H, W), generator=g).float()
+    else:  # coordinates landing exactly on / just around the image border
+        fl = torch.zeros(B, 2, H, W)
+        fl[:, 0] = -torch.arange(W).float().view(1, 1, W) + torch.tensor([0.0, -0.25, W - 1.0, W - 0.75])[
+            torch.randint(0, 4, (B, H, W), generator=g)]
+        fl[:, 1] = -torch.arange(H).float().view(1, H, 1) + torch.tensor([0.0, -0.25, H - 1.0, H - 0.75])[
+            torch.randint(0, 4, (B, H, W), generator=g)]
+    xn, fn, gn = x.numpy(), fl.numpy(), go.numpy()
+    check(ops.warp_fwd(x.cuda(), fl.cuda(), pad), c_oracle.warp_fwd(xn, fn, pad), "out")
+    ogx, ogf = c_oracle.warp_bwd(xn, fn, gn, pad)
+    for atomic in (False, True):
+        gx, gf = ops.warp_bwd(x.cuda(), fl.cuda(), go.cuda(), pad, atomic=atomic)
+        check(gx, ogx, f"gx(atomic={atomic})")
+        check(gf, ogf, f"gflow(atomic={atomic})")
+    none, gf = ops.warp_bwd(x.cuda(), fl.cuda(), go.cuda(), pad, need_gx=False)
+    assert none is None
+    check(gf, ogf, "gflow only")
+    gx, none = ops.warp_bwd(x.cuda(), fl.cuda(), go.cuda(), pad, need_gflow=False)
+    assert none is None
+    check(gx, ogx, "gx only")
+
+
+def test_warp_bwd_collapse_overflows_tap_lists(usf):
+    """Every pixel flows far out of the image: border padding piles all taps onto the border
+    pixels (far more than the 8 list slots each), exercising the overflow side list."""
+    from oracle import c_oracle
+    ops = usf.ops_mod
+    B, C, H, W = 1, 8, 16, 40
+    g = torch.Generator().manual_seed(11)
+    x, go = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
+    fl = torch.full((B, 2, H, W), 1000.0)
+    fl[:, :, : H // 2] = torch.randn(B, 2, H // 2, W, generator=g) * 0.3 + 5.5  # pile onto few targets
+    ogx, ogf = c_oracle.warp_bwd(x.numpy(), fl.numpy(), go.numpy(), "border")
+    gx, gf = ops.warp_bwd(x.cuda(), fl.cuda(), go.cuda(), "border")
+    check(gx, ogx, "gx with overflow")
+    check(gf, ogf, "gflow with overflow")
+
+
+def test_warp_list_path_is_deterministic(usf):
+    ops = usf.ops_mod
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 32, 64, 208, generator=g).cuda()
+    go = torch.randn(2, 32, 64, 208, generator=g).cuda()
+    fl = (torch.randn(2, 2, 64, 208, generator=g) * 1.0).cuda()
+    a, _ = ops.warp_bwd(x, fl, go, "zeros", need_gflow=False)
+    b, _ = ops.warp_bwd(x, fl, go, "zeros", need_gflow=False)
+    # sigma = 1 px: (almost) no target exceeds its 8 slots, so the sum order is fixed
+    assert (a != b).float().mean().item() < 1e-4
+
+
+# --------------------------------------------------------------------------------------------
+# size-independent properties at the bench sizes
+# --------------------------------------------------------------------------------------------
+def test_corr_adjoint_identity_full_size(usf):
+    """<gO, corr(x1,x2)> is bilinear: it equals <gx1, x1> and <gx2, x2> exactly in exact arithmetic."""
+    ops = usf.ops_mod
+    for shape in [(8, 32, 64, 208), (8, 64, 32, 104), (8, 96, 16, 52), (8, 128, 8, 26), (8, 192, 4, 13)]:
+        B, C, H, W = shape
+        g = torch.Generator().manual_seed(C)
+        x1, x2 = torch.randn(shape, generator=g).cuda(), torch.randn(shape, generator=g).cuda()
+        go = torch.randn(B, 81, H, W, generator=g).cuda()
+        out = ops.corr_fwd(x1, x2)
+        g1, g2 = ops.corr_bwd(x1, x2, go)
+        lhs = (go.double() * out.double()).sum().item()
+        scale = (go.double().abs() * out.double().abs()).sum().item()
+        assert abs(lhs - (g1.double() * x1.double()).sum().item()) <= 1e-6 * scale
+        assert abs(lhs - (g2.double() * x2.double()).sum().item()) <= 1e-6 * scale
+
+
+def test_corr_swap_symmetry(usf):
+    """corr(x1,x2)[k(d)](p) == corr(x2,x1)[k(-d)](p+d) wherever both are defined."""
+    ops = usf.ops_mod
+    g = torch.Generator().manual_seed(21)
+    x1, x2 = torch.randn(2, 64, 32, 104, generator=g).cuda(), torch.randn(2, 64, 32, 104, generator=g).cuda()
+    a, b = ops.corr_fwd(x1, x2), ops.corr_fwd(x2, x1)
+    H, W = 32, 104
+    for dy, dx in [(-4, -4), (0, 3), (2, -1), (4, 4)]:
+        k, kneg = (dy + 4) * 9 + dx + 4, (-dy + 4) * 9 - dx + 4
+        ys, xs = slice(max(0, -dy), min(H, H - dy)), slice(max(0, -dx), min(W, W - dx))
+        yt = slice(ys.start + dy, ys.stop + dy)
+        xt = slice(xs.start + dx, xs.stop + dx)
+        assert torch.allclose(a[:, k, ys, xs], b[:, kneg, yt, xt], rtol=1e-5, atol=1e-6)
+
+
+def test_warp_identity_and_integer_shift_full_size(usf):
+    ops = usf.ops_mod
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(8, 3, 256, 832, generator=g).cuda()
+    zero = torch.zeros(8, 2, 256, 832).cuda()
+    y = ops.warp_fwd(x, zero, "border")
+    assert max_norm_err(y.cpu().numpy(), x.cpu().numpy()) < 2e-4  # coordinate round trip: <= 6e-5 px at W=832
+    fl = zero.clone()
+    fl[:, 0] = 2.0
+    fl[:, 1] = -1.0
+    y = ops.warp_fwd(x, fl, "zeros")
+    want = torch.zeros_like(x)
+    want[:, :, 1:, :-2] = x[:, :, :-1, 2:]
+    assert max_norm_err(y.cpu().numpy(), want.cpu().numpy()) < 2e-4
+
+
+def test_warp_adjoint_identity_full_size(usf):
+    """warp is linear in x: <gO, warp(x)> == <gx, x>."""
+    ops = usf.ops_mod
+    for shape, pad in [((8, 32, 64, 208), "border"), ((8, 3, 256, 832), "zeros")]:
+        B, C, H, W = shape
+        g = torch.Generator().manual_seed(C + H)
+        x, go = torch.randn(shape, generator=g).cuda(), torch.randn(shape, generator=g).cuda()
+        fl = (3.0 * torch.randn(B, 2, H, W, generator=g)).cuda()
+        y = ops.warp_fwd(x, fl, pad)
+        gx, _ = ops.warp_bwd(x, fl, go, pad, need_gflow=False)
+        lhs = (go.double() * y.double()).sum().item()
+        rhs = (gx.double() * x.double()).sum().item()
+        scale = (go.double().abs() * y.double().abs()).sum().item()
+        assert abs(lhs - rhs) <= 1e-6 * scale
+
+
+# --------------------------------------------------------------------------------------------
+# the torch port (what the reference runs) on the SAME device: ATen CUDA kernels as 2nd opinion
+# --------------------------------------------------------------------------------------------
+def test_against_torch_port_on_cuda(usf):
+    """One decoder level (warp -> corr, fwd+bwd) against the ATen CUDA kernels the reference would
+    run on this GPU.  ATen's CUDA `tensor / scalar` multiplies by the reciprocal while the CPU kernel
+    divides, so both coordinate flavours are measured; the flavour matching the device must agree to
+    the parity budget (the other one shows the reference's own CPU-vs-GPU spread)."""
+    import json
+    import os
+    from oracle import torch_port
+    g = torch.Generator().manual_seed(31)
+    x1 = torch.randn(2, 64, 32, 104, generator=g).cuda().requires_grad_(True)
+    x2 = torch.randn(2, 64, 32, 104, generator=g).cuda().requires_grad_(True)
+    fl = (2.0 * torch.randn(2, 2, 32, 104, generator=g)).cuda().requires_grad_(True)
+    go = torch.randn(2, 81, 32, 104, generator=g).cuda()
+    corr = usf.Correlation(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1, corr_multiply=1)
+    ref = torch_port.cost_volume(x1, torch_port.flow_warp(x2, fl))
+    ref.backward(go)
+    want = [t.detach().cpu().numpy() for t in (ref, x1.grad, x2.grad, fl.grad)]
+    errs = {}
+    for recip in (False, True):
+        for t in (x1, x2, fl):
+            t.grad = None
+        out = corr(x1, usf.flow_warp(x2, fl, coord_reciprocal=recip))
+        out.backward(go)
+        got = [t.detach().cpu().numpy() for t in (out, x1.grad, x2.grad, fl.grad)]
+        errs["reciprocal" if recip else "divide"] = {
+            n: max(rel_l2(a, b), max_norm_err(a, b)) for n, a, b in zip(["out", "gx1", "gx2", "gflow"], got, want)}
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/coord_mode_vs_aten_cuda.json", "w") as f:
+        json.dump(errs, f, indent=1)
+    best = min(errs.values(), key=lambda e: max(e.values()))
+    assert max(best.values()) <= 2e-5, errs
+
+
+# --------------------------------------------------------------------------------------------
+# boundary behaviour
+# --------------------------------------------------------------------------------------------
+def test_errors_are_loud(usf):
+    ops = usf.ops_mod
+    x = torch.zeros(1, 4, 8, 8).cuda()
+    with pytest.raises(ValueError):
+        ops.corr_fwd(x, torch.zeros(1, 4, 8, 9).cuda())
+    with pytest.raises(RuntimeError):
+        ops.corr_fwd(x, torch.zeros(1, 4, 8, 8))  # CPU tensor: no fallback
+    with pytest.raises(ValueError):
+        ops.warp_fwd(x, torch.zeros(1, 3, 8, 8).cuda())
+    with pytest.raises(ValueError):
+        ops.warp_fwd(torch.zeros(1, 4, 1, 8).cuda(), torch.zeros(1, 2, 1, 8).cuda())
+    with pytest.raises(NotImplementedError):
+        usf.flow_warp(x, torch.zeros(1, 2, 8, 8).cuda(), mode="nearest")
+    with pytest.raises(NotImplementedError):
+        ops.corr_fwd(x.half(), x.half())
+
+
+def test_cuda_graph_capture_of_a_step(usf):
+    """The whole hot-path step is capturable (no allocation, no sync, no H2D inside)."""
+    from unsamflow_b200.hotpath import HotPathStep
+    step = HotPathStep(1, 64, 208, flow_sigma=1.5)
+    step.run()
+    torch.cuda.synchronize()
+    eager = {k: v.clone() for k, v in step.t.items() if k.startswith(("corr.", "gx1.", "gflow.", "glflow."))}
+    for v in eager:
+        step.t[v].zero_()
+    graph = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        step.run()
+    torch.cuda.current_stream().wait_stream(s)
+    with torch.cuda.graph(graph):
+        step.run()
+    for v in eager:
+        step.t[v].zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    for k, v in eager.items():
+        assert torch.allclose(step.t[k], v, rtol=1e-5, atol=1e-6), k

@@ -1,0 +1,79 @@
+"""Host-side mirror of the reference interface: constructor / call-signature behaviour, loud
+failures without a GPU, and the hot-path shape and byte accounting."""
+import inspect
+
+import pytest
+import torch
+
+import unsamflow_b200
+from unsamflow_b200 import hotpath
+
+
+def test_correlation_ctor_matches_reference_call_site():
+    # models/pwclite.py:208-215
+    m = unsamflow_b200.Correlation(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1,
+                                   corr_multiply=1)
+    assert (m.pad_size, m.kernel_size, m.max_displacement, m.stride1, m.stride2) == (4, 1, 4, 1, 1)
+    assert m.output_dim == 9 and not list(m.parameters())
+    # correlation_native.py:7 style (extra kwargs swallowed)
+    unsamflow_b200.Correlation(max_displacement=4, kernel_size=1, stride1=1, stride2=1, corr_multiply=1)
+    for bad in (dict(max_displacement=3), dict(kernel_size=3), dict(stride2=2), dict(pad_size=3)):
+        with pytest.raises(NotImplementedError):
+            unsamflow_b200.Correlation(**bad)
+
+
+def test_flow_warp_signature_matches_reference():
+    # utils/warp_utils.py:97: flow_warp(x, flow12, pad="border", mode="bilinear")
+    params = list(inspect.signature(unsamflow_b200.flow_warp).parameters.values())
+    assert [p.name for p in params[:4]] == ["x", "flow12", "pad", "mode"]
+    assert params[2].default == "border" and params[3].default == "bilinear"
+    with pytest.raises(NotImplementedError):
+        unsamflow_b200.flow_warp(torch.zeros(1, 1, 2, 2), torch.zeros(1, 2, 2, 2), mode="nearest")
+    with pytest.raises(ValueError):
+        unsamflow_b200.flow_warp(torch.zeros(1, 1, 2, 2), torch.zeros(1, 2, 2, 2), pad="reflection")
+
+
+def test_no_cpu_fallback():
+    x = torch.zeros(1, 2, 4, 4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        unsamflow_b200.Correlation()(x, x)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        unsamflow_b200.flow_warp(x, torch.zeros(1, 2, 4, 4))
+
+
+def test_product_never_imports_the_oracle():
+    import os
+    import re
+    root = os.path.dirname(unsamflow_b200.__file__)
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "usf_oracle" not in text, f
+
+
+def test_pyramid_shapes_match_survey():
+    assert hotpath.pyramid_shapes(256, 832) == [(192, 4, 13), (128, 8, 26), (96, 16, 52), (64, 32, 104),
+                                                (32, 64, 208)]
+    assert hotpath.pyramid_shapes(384, 832) == [(192, 6, 13), (128, 12, 26), (96, 24, 52), (64, 48, 104),
+                                                (32, 96, 208)]
+    assert hotpath.pyramid_shapes(448, 1024)[0] == (192, 7, 16)
+    assert hotpath.pyramid_shapes(192, 640)[0] == (192, 3, 10)
+    assert hotpath.pyramid_shapes(320, 704)[-1] == (32, 80, 176)
+    assert hotpath.loss_shapes(256, 832) == [(3, 256, 832), (3, 128, 416), (3, 64, 208), (3, 32, 104)]
+
+
+def test_algorithmic_bytes_match_baseline_md():
+    # KITTI pyramid B=1 11.8 / 17.8 MB, B=8 94.3 / 142.7 MB; Sintel B=4 70.7 / 107.0 MB
+    def tot(fn, B, H, W):
+        return sum(fn(B, *s) for s in hotpath.pyramid_shapes(H, W)) / 1e6
+    assert round(tot(hotpath.corr_fwd_bytes, 1, 256, 832), 1) == 11.8
+    assert round(tot(hotpath.corr_bwd_bytes, 1, 256, 832), 1) == 17.8
+    assert round(tot(hotpath.corr_fwd_bytes, 8, 256, 832), 1) == 94.3
+    assert round(tot(hotpath.corr_bwd_bytes, 8, 256, 832), 1) == 142.7
+    assert round(tot(hotpath.corr_fwd_bytes, 4, 384, 832), 1) == 70.7
+    assert round(tot(hotpath.corr_bwd_bytes, 4, 384, 832), 1) == 107.0
+    assert hotpath.warp_fwd_bytes(1, 32, 64, 208) == (2 * 32 + 2) * 4 * 64 * 208
+    assert hotpath.warp_bwd_bytes(1, 3, 256, 832, need_gx=False) == (2 * 3 + 4) * 4 * 256 * 832
+    assert round(tot(hotpath.corr_fwd_flops, 8, 256, 832) / 1e3, 2) == 0.98  # GFLOP

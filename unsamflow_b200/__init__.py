@@ -1,0 +1,13 @@
+"""unsamflow_b200 -- B200-native (sm_100a) correlation cost volume + flow_warp for PWC-Lite.
+
+Drop-in for the hot path of turswiming/UnSAMFlow:
+    from unsamflow_b200 import Correlation, flow_warp
+replaces `models/correlation_package/correlation.Correlation` (or correlation_native) and
+`utils.warp_utils.flow_warp`.  The math runs in hand-written CUDA kernels behind the C ABI in
+include/unsamflow_b200.h; there is no CPU or PyTorch fallback.
+"""
+from .correlation import Correlation, CorrelationFunction  # noqa: F401
+from .warp import FlowWarpFunction, flow_warp  # noqa: F401
+
+__all__ = ["Correlation", "CorrelationFunction", "FlowWarpFunction", "flow_warp"]
+__version__ = "0.1.0"

@@ -1,0 +1,71 @@
+"""ctypes binding of libunsamflow_b200.so (the C ABI in include/unsamflow_b200.h).
+
+There is NO fallback: if the CUDA library is missing or fails to load, importing the
+ops raises.  Nothing here touches oracle/.
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libunsamflow_b200.so")
+
+ABI_VERSION = 1
+F32, BF16 = 0, 1
+PAD_BORDER, PAD_ZEROS = 0, 1
+FLAG_LEAKY_RELU = 1
+FLAG_COORD_RECIPROCAL = 2
+FLAG_WARP_BWD_ATOMIC = 4
+
+# every symbol include/unsamflow_b200.h declares (tests/test_abi.py checks header <-> library <-> this list)
+SYMBOLS = (
+    "usf_abi_version", "usf_status_string", "usf_last_cuda_error", "usf_launch_count",
+    "usf_reset_launch_count", "usf_corr_fwd", "usf_corr_bwd", "usf_warp_fwd",
+    "usf_warp_bwd_workspace_bytes", "usf_warp_bwd",
+)
+
+_lib = None
+
+
+class UsfError(RuntimeError):
+    """Raised when a C-ABI call returns non-zero (the reference raises RuntimeError via AT_ERROR,
+    models/correlation_package/correlation_cuda.cc:80-82)."""
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m unsamflow_b200.build` "
+            "(or __graft_entry__.build()). unsamflow_b200 has no CPU or PyTorch fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i, u, f, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint, ctypes.c_float, ctypes.c_size_t
+    L.usf_abi_version.restype = i
+    L.usf_status_string.restype = ctypes.c_char_p
+    L.usf_status_string.argtypes = [i]
+    L.usf_last_cuda_error.restype = i
+    L.usf_launch_count.restype = ctypes.c_ulonglong
+    L.usf_reset_launch_count.restype = None
+    L.usf_corr_fwd.restype = i
+    L.usf_corr_fwd.argtypes = [vp, vp, vp, i, i, i, i, i, i, u, f, vp]
+    L.usf_corr_bwd.restype = i
+    L.usf_corr_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, u, vp]
+    L.usf_warp_fwd.restype = i
+    L.usf_warp_fwd.argtypes = [vp, vp, vp, i, i, i, i, i, i, u, vp]
+    L.usf_warp_bwd_workspace_bytes.restype = sz
+    L.usf_warp_bwd_workspace_bytes.argtypes = [i, i, i, i, u]
+    L.usf_warp_bwd.restype = i
+    L.usf_warp_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, u, vp, sz, vp]
+    if L.usf_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI {L.usf_abi_version()} != expected {ABI_VERSION}; rebuild")
+    _lib = L
+    return L
+
+
+def check(status, what):
+    if status != 0:
+        L = load()
+        msg = L.usf_status_string(status).decode()
+        extra = f" (cudaError {L.usf_last_cuda_error()})" if status == -4 else ""
+        raise UsfError(f"{what}: {msg}{extra}")

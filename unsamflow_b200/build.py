@@ -1,0 +1,63 @@
+"""In-tree nvcc build of libunsamflow_b200.so (sm_100a only, no torch headers needed).
+
+The library is the C-ABI product (include/unsamflow_b200.h); it is built next to the
+package so that it travels to the GPU box with the source snapshot.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG, "csrc")
+LIB_DIR = os.path.join(PKG, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libunsamflow_b200.so")
+SOURCES = ["api.cu", "corr_fwd.cu", "corr_bwd.cu", "warp.cu"]
+HEADERS = ["common.cuh", os.path.join("..", "..", "include", "unsamflow_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xptxas=-v",
+    "-Xcompiler", "-fPIC,-O3,-Wall",
+    "-shared", "-cudart", "static",
+]
+
+
+def find_nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: cannot build libunsamflow_b200.so")
+
+
+def is_stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every CUDA source for sm_100a into one shared library. Returns its path."""
+    if not force and not is_stale():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [find_nvcc()] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    env = dict(os.environ)
+    # an inherited CC/CXX may point at a toolchain nvcc cannot drive; use the system g++
+    proc = subprocess.run(cmd + ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else cmd,
+                          env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    log_path = os.path.join(LIB_DIR, "build.log")
+    with open(log_path, "w") as f:
+        f.write(" ".join(cmd) + "\n" + proc.stdout)
+    if verbose or proc.returncode != 0:
+        sys.stderr.write(proc.stdout)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed (exit {proc.returncode}); see {log_path}")
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,122 @@
+// api.cu -- the extern "C" boundary declared in include/unsamflow_b200.h.
+// Validates arguments, dispatches on dtype, never allocates, never synchronises.
+#include "common.cuh"
+
+namespace usf {
+
+int corr_fwd_f32(const float *, const float *, float *, int, int, int, int, unsigned, float, cudaStream_t);
+int corr_bwd_f32(const float *, const float *, const float *, float *, float *, int, int, int, int,
+                 cudaStream_t);
+int warp_fwd_f32(const float *, const float *, float *, int, int, int, int, int, unsigned, cudaStream_t);
+int warp_bwd_f32(const float *, const float *, const float *, float *, float *, int, int, int, int, int,
+                 unsigned, void *, size_t, cudaStream_t);
+size_t warp_bwd_workspace_bytes(size_t N);
+
+static thread_local int tl_cuda_error = 0;
+static thread_local unsigned long long tl_launches = 0;
+
+void note_cuda_error(cudaError_t e) { tl_cuda_error = (int)e; }
+
+int note_launch(cudaError_t e) {
+    if (e != cudaSuccess) {
+        tl_cuda_error = (int)e;
+        return USF_ERR_CUDA;
+    }
+    ++tl_launches;
+    return USF_OK;
+}
+
+static int check_dims(int B, int C, int H, int W, int chan_max) {
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0) return USF_ERR_BAD_SHAPE;
+    const long long plane = (long long)H * W;
+    const int cm = C > chan_max ? C : chan_max;
+    // 32-bit index bound on the largest tensor the call touches
+    if ((long long)B * cm * plane > 2147483647LL) return USF_ERR_BAD_SHAPE;
+    return USF_OK;
+}
+
+}  // namespace usf
+
+using namespace usf;
+
+extern "C" {
+
+int usf_abi_version(void) { return USF_ABI_VERSION; }
+
+const char *usf_status_string(int status) {
+    switch (status) {
+        case USF_OK: return "ok";
+        case USF_ERR_BAD_SHAPE: return "bad shape (non-positive dim, H or W < 2 for warp, or > 2^31-1 elements)";
+        case USF_ERR_BAD_ARG: return "bad argument (null pointer, unknown dtype/pad/flag, or max_disp != 4)";
+        case USF_ERR_WORKSPACE: return "workspace missing or too small (see usf_warp_bwd_workspace_bytes)";
+        case USF_ERR_CUDA: return "CUDA call failed (see usf_last_cuda_error)";
+        case USF_ERR_UNSUPPORTED: return "not implemented in this build";
+        default: return "unknown status";
+    }
+}
+
+int usf_last_cuda_error(void) { return tl_cuda_error; }
+unsigned long long usf_launch_count(void) { return tl_launches; }
+void usf_reset_launch_count(void) { tl_launches = 0; }
+
+int usf_corr_fwd(const void *x1, const void *x2, void *out, int B, int C, int H, int W, int max_disp,
+                 int dtype, unsigned flags, float leaky_slope, void *stream) {
+    if (!x1 || !x2 || !out || max_disp != kMaxDisp) return USF_ERR_BAD_ARG;
+    if (flags & ~USF_FLAG_LEAKY_RELU) return USF_ERR_BAD_ARG;
+    if (int st = check_dims(B, C, H, W, kK)) return st;
+    if (dtype == USF_F32)
+        return corr_fwd_f32((const float *)x1, (const float *)x2, (float *)out, B, C, H, W, flags, leaky_slope,
+                            (cudaStream_t)stream);
+    if (dtype == USF_BF16) return USF_ERR_UNSUPPORTED;
+    return USF_ERR_BAD_ARG;
+}
+
+int usf_corr_bwd(const void *x1, const void *x2, const void *gout, void *gx1, void *gx2, int B, int C,
+                 int H, int W, int max_disp, int dtype, unsigned flags, void *stream) {
+    if (!x1 || !x2 || !gout || max_disp != kMaxDisp || flags != 0) return USF_ERR_BAD_ARG;
+    if (int st = check_dims(B, C, H, W, kK)) return st;
+    if (!gx1 && !gx2) return USF_OK;
+    if (dtype == USF_F32)
+        return corr_bwd_f32((const float *)x1, (const float *)x2, (const float *)gout, (float *)gx1,
+                            (float *)gx2, B, C, H, W, (cudaStream_t)stream);
+    if (dtype == USF_BF16) return USF_ERR_UNSUPPORTED;
+    return USF_ERR_BAD_ARG;
+}
+
+int usf_warp_fwd(const void *x, const float *flow, void *out, int B, int C, int H, int W, int pad_mode,
+                 int dtype, unsigned flags, void *stream) {
+    if (!x || !flow || !out) return USF_ERR_BAD_ARG;
+    if (pad_mode != USF_PAD_BORDER && pad_mode != USF_PAD_ZEROS) return USF_ERR_BAD_ARG;
+    if (flags & ~USF_FLAG_COORD_RECIPROCAL) return USF_ERR_BAD_ARG;
+    if (int st = check_dims(B, C, H, W, 2)) return st;
+    if (H < 2 || W < 2) return USF_ERR_BAD_SHAPE;  // the reference divides by (size-1): utils/warp_utils.py:21-22
+    if (dtype == USF_F32)
+        return warp_fwd_f32((const float *)x, flow, (float *)out, B, C, H, W, pad_mode, flags,
+                            (cudaStream_t)stream);
+    if (dtype == USF_BF16) return USF_ERR_UNSUPPORTED;
+    return USF_ERR_BAD_ARG;
+}
+
+size_t usf_warp_bwd_workspace_bytes(int B, int C, int H, int W, unsigned flags) {
+    (void)C;
+    if (B <= 0 || H <= 0 || W <= 0 || (flags & USF_FLAG_WARP_BWD_ATOMIC)) return 0;
+    return warp_bwd_workspace_bytes((size_t)B * H * W);
+}
+
+int usf_warp_bwd(const void *x, const float *flow, const void *gout, void *gx, float *gflow, int B, int C,
+                 int H, int W, int pad_mode, int dtype, unsigned flags, void *workspace, size_t workspace_bytes,
+                 void *stream) {
+    if (!x || !flow || !gout) return USF_ERR_BAD_ARG;
+    if (pad_mode != USF_PAD_BORDER && pad_mode != USF_PAD_ZEROS) return USF_ERR_BAD_ARG;
+    if (flags & ~(USF_FLAG_COORD_RECIPROCAL | USF_FLAG_WARP_BWD_ATOMIC)) return USF_ERR_BAD_ARG;
+    if (int st = check_dims(B, C, H, W, 2)) return st;
+    if (H < 2 || W < 2) return USF_ERR_BAD_SHAPE;
+    if (!gx && !gflow) return USF_OK;
+    if (dtype == USF_F32)
+        return warp_bwd_f32((const float *)x, flow, (const float *)gout, (float *)gx, gflow, B, C, H, W,
+                            pad_mode, flags, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (dtype == USF_BF16) return USF_ERR_UNSUPPORTED;
+    return USF_ERR_BAD_ARG;
+}
+
+}  // extern "C"

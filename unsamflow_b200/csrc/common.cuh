@@ -1,0 +1,51 @@
+// common.cuh -- shared device helpers for the corr / warp kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/unsamflow_b200.h"
+
+namespace usf {
+
+constexpr int kMaxDisp = 4;            // PWC-Lite search range (models/pwclite.py:182)
+constexpr int kD = 2 * kMaxDisp + 1;   // 9
+constexpr int kK = kD * kD;            // 81 displacement channels
+
+// ---- host-side bookkeeping (api.cu) ---------------------------------------
+int note_launch(cudaError_t e);        // counts a launch, records e; returns usf_status
+void note_cuda_error(cudaError_t e);
+
+// ---- cp.async (LDGSTS) ------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+// 16-byte copy, bypassing L1; src_bytes == 0 zero-fills the destination.
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem),
+                 "r"(src_bytes)
+                 : "memory");
+}
+// 4-byte copy; src_bytes == 0 zero-fills.
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(smem_u32(smem)), "l"(gmem),
+                 "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ float4 lds128(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+
+__device__ __forceinline__ void st_global_cs(float *p, float v) {
+    asm volatile("st.global.cs.f32 [%0], %1;\n" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_global_cs4(float *p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+}  // namespace usf

@@ -1,0 +1,216 @@
+// corr_bwd.cu -- cost-volume backward for sm_100a (fp32 storage, fp32 FFMA), atomic-free.
+//
+// Replaces: correlation_cuda.backward (models/correlation_package/correlation_cuda.cc:88-165 ->
+// channels_first x2 + per-batch-item loops of correlation_backward_input1 / _input2,
+// correlation_cuda_kernel.cu:116-300, :458-513), i.e. autograd of models/correlation_native.py:13-23:
+//     gx1[b,c,y,x] = (1/C) sum_{dy,dx} gO[b,k(dy,dx),y,x]       * x2[b,c,y+dy,x+dx]
+//     gx2[b,c,y,x] = (1/C) sum_{dy,dx} gO[b,k(dy,dx),y-dy,x-dx] * x1[b,c,y-dy,x-dx]
+// With e = -d the second sum reads  sum_e gO[b,k(-e),y+ey,x+ex] * x1[b,c,y+ey,x+ex]  and
+// k(-e) = 80 - k(e): both gradients are the SAME gather  out[c,p] = sum_e G[e,p] * X[c,p+e],
+// they only differ in how the G tile is fetched (gx2: channel 80-k, shifted by e, zero outside).
+//
+// One kernel template does both: a CTA owns an 8x32 pixel tile and 32 channels (4 warps x 8
+// channels), stages the X halo tile (16x40 per channel) once and streams G one dy at a time
+// through a 2-stage cp.async ring.  A thread owns 8 pixels x 8 channels (64 accumulators) and
+// keeps the 9x8 G values of the current dy in registers: per (dy, channel) it issues 4 LDS.128
+// for 72 FFMA.  Every output element is written exactly once: no atomics, no zero-fill, one
+// launch per gradient for the whole batch (the reference launches 2*B kernels).
+#include "common.cuh"
+
+namespace usf {
+namespace {
+
+constexpr int TH = 8, TW = 32;
+constexpr int CG = 32;                    // channels per CTA
+constexpr int CT = 8;                     // channels per thread
+constexpr int NTHREADS = 32 * (CG / CT);  // 128
+constexpr int XR = TH + 2 * kMaxDisp;     // 16 halo rows
+constexpr int XW = TW + 2 * kMaxDisp;     // 40 halo cols
+constexpr int XS = 44;                    // halo row stride (11 chunks)
+constexpr int GS = 36;                    // G tile row stride (9 chunks)
+constexpr int X_FLOATS = CG * XR * XS;    // 22528
+constexpr int G_STAGE = kD * TH * GS;     // 2592
+constexpr int SMEM_BYTES = (X_FLOATS + 2 * G_STAGE) * 4;  // 110848
+
+template <bool VEC>
+__device__ __forceinline__ void load_x_tile(float *__restrict__ xs, const float *__restrict__ xb, int c0,
+                                            int C, int H, int W, int y0, int x0, int tid) {
+    constexpr int CHUNKS = CG * XR * (XW / 4);  // 5120
+    for (int i = tid; i < CHUNKS; i += NTHREADS) {
+        const int c = i / (XR * 10);
+        const int rem = i - c * (XR * 10);
+        const int r = rem / 10, ch = rem - r * 10;
+        const int cc = c0 + c, gy = y0 - kMaxDisp + r, gx = x0 - kMaxDisp + 4 * ch;
+        float *dst = xs + (c * XR + r) * XS + 4 * ch;
+        const bool rowok = (cc < C) && (gy >= 0) && (gy < H);
+        const float *src = xb + ((size_t)cc * H + gy) * W + gx;
+        if (VEC) {
+            const bool ok = rowok && (gx >= 0) && (gx < W);
+            cp_async16(dst, ok ? src : xb, ok ? 16 : 0);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool ok = rowok && (gx + e >= 0) && (gx + e < W);
+                cp_async4(dst + e, ok ? src + e : xb, ok ? 4 : 0);
+            }
+        }
+    }
+}
+
+// G tile of one dy (9 dx): gs[dxi][r][col].
+//   gx1: G[dxi][r][col] = gO[k = dyi*9+dxi][y0+r][x0+col]
+//   gx2: G[dxi][r][col] = gO[80-k][y0+r+ey][x0+col+ex],  ey = dyi-4, ex = dxi-4, zero outside
+template <bool GX2, bool VEC>
+__device__ __forceinline__ void load_g_stage(float *__restrict__ gs, const float *__restrict__ gob, int dyi,
+                                             int H, int W, int y0, int x0, int tid) {
+    constexpr int CHUNKS = kD * TH * (TW / 4);  // 576
+    for (int i = tid; i < CHUNKS; i += NTHREADS) {
+        const int dxi = i >> 6, r = (i >> 3) & 7, ch = i & 7;
+        const int k = dyi * kD + dxi;
+        float *dst = gs + (dxi * TH + r) * GS + 4 * ch;
+        if (!GX2) {
+            const int gy = y0 + r, gx = x0 + 4 * ch;
+            const float *src = gob + ((size_t)k * H + gy) * W + gx;
+            if (VEC) {
+                const bool ok = (gy < H) && (gx < W);
+                cp_async16(dst, ok ? src : gob, ok ? 16 : 0);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool ok = (gy < H) && (gx + e < W);
+                    cp_async4(dst + e, ok ? src + e : gob, ok ? 4 : 0);
+                }
+            }
+        } else {
+            const int ex = dxi - kMaxDisp;
+            const int gy = y0 + r + dyi - kMaxDisp, gx = x0 + 4 * ch + ex;
+            const bool rowok = (gy >= 0) && (gy < H);
+            const float *src = gob + ((size_t)(kK - 1 - k) * H + gy) * W + gx;
+            if (VEC && (ex & 3) == 0) {
+                const bool ok = rowok && (gx >= 0) && (gx < W);
+                cp_async16(dst, ok ? src : gob, ok ? 16 : 0);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const bool ok = rowok && (gx + e >= 0) && (gx + e < W);
+                    cp_async4(dst + e, ok ? src + e : gob, ok ? 4 : 0);
+                }
+            }
+        }
+    }
+}
+
+// grid = (tiles_x, tiles_y, B * ngroups)
+template <bool GX2, bool VEC>
+__global__ void __launch_bounds__(NTHREADS, 2)
+corr_bwd_gather(const float *__restrict__ xin, const float *__restrict__ gout, float *__restrict__ gx, int C,
+                int H, int W, int ngroups, float rc) {
+    extern __shared__ __align__(16) float smem[];
+    float *xs = smem;
+    float *gsm = smem + X_FLOATS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = lane >> 2, q = lane & 3;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int b = blockIdx.z / ngroups, cg = blockIdx.z - b * ngroups;
+    const int c0 = cg * CG;
+    const float *xb = xin + (size_t)b * C * H * W;
+    const float *gob = gout + (size_t)b * kK * H * W;
+
+    load_x_tile<VEC>(xs, xb, c0, C, H, W, y0, x0, tid);
+    load_g_stage<GX2, VEC>(gsm, gob, 0, H, W, y0, x0, tid);
+    cp_async_commit();
+    load_g_stage<GX2, VEC>(gsm + G_STAGE, gob, 1, H, W, y0, x0, tid);
+    cp_async_commit();
+
+    float acc[CT][8];
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
+
+    const float *xw = xs + (warp * CT * XR + r) * XS + 8 * q;
+#pragma unroll 1
+    for (int dyi = 0; dyi < kD; ++dyi) {
+        cp_async_wait<1>();
+        __syncthreads();
+        const float *gs = gsm + (dyi & 1) * G_STAGE + r * GS + 8 * q;
+        float g[kD][8];
+#pragma unroll
+        for (int dx = 0; dx < kD; ++dx) {
+            const float4 g0 = lds128(gs + dx * TH * GS), g1 = lds128(gs + dx * TH * GS + 4);
+            g[dx][0] = g0.x; g[dx][1] = g0.y; g[dx][2] = g0.z; g[dx][3] = g0.w;
+            g[dx][4] = g1.x; g[dx][5] = g1.y; g[dx][6] = g1.z; g[dx][7] = g1.w;
+        }
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const float *p = xw + (c * XR + dyi) * XS;
+            const float4 w0 = lds128(p), w1 = lds128(p + 4), w2 = lds128(p + 8), w3 = lds128(p + 12);
+            const float w[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
+                                 w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+            for (int dx = 0; dx < kD; ++dx)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(g[dx][i], w[dx + i], acc[c][i]);
+        }
+        __syncthreads();  // stage (dyi & 1) fully consumed
+        if (dyi + 2 < kD) load_g_stage<GX2, VEC>(gsm + (dyi & 1) * G_STAGE, gob, dyi + 2, H, W, y0, x0, tid);
+        cp_async_commit();
+    }
+
+    const int gy = y0 + r, gxx = x0 + 8 * q;
+    if (gy >= H) return;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+        const int cc = c0 + warp * CT + c;
+        if (cc >= C) break;
+        float *o = gx + (((size_t)b * C + cc) * H + gy) * W + gxx;
+        if (VEC) {
+            if (gxx < W)
+                *reinterpret_cast<float4 *>(o) =
+                    make_float4(acc[c][0] * rc, acc[c][1] * rc, acc[c][2] * rc, acc[c][3] * rc);
+            if (gxx + 4 < W)
+                *reinterpret_cast<float4 *>(o + 4) =
+                    make_float4(acc[c][4] * rc, acc[c][5] * rc, acc[c][6] * rc, acc[c][7] * rc);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (gxx + i < W) o[i] = acc[c][i] * rc;
+        }
+    }
+}
+
+template <bool GX2, bool VEC>
+cudaError_t launch(const float *xin, const float *gout, float *gx, int B, int C, int H, int W,
+                   cudaStream_t stream) {
+    static cudaError_t once = cudaFuncSetAttribute(corr_bwd_gather<GX2, VEC>,
+                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    (void)once;
+    const int ngroups = (C + CG - 1) / CG;
+    dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B * ngroups);
+    corr_bwd_gather<GX2, VEC><<<grid, NTHREADS, SMEM_BYTES, stream>>>(xin, gout, gx, C, H, W, ngroups,
+                                                                      1.0f / (float)C);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+int corr_bwd_f32(const float *x1, const float *x2, const float *gout, float *gx1, float *gx2, int B, int C,
+                 int H, int W, cudaStream_t stream) {
+    const bool vec = (W % 4 == 0) &&
+                     (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)gout | (uintptr_t)gx1 | (uintptr_t)gx2) % 16 == 0);
+    int st = USF_OK;
+    if (gx1) {
+        cudaError_t e = vec ? launch<false, true>(x2, gout, gx1, B, C, H, W, stream)
+                            : launch<false, false>(x2, gout, gx1, B, C, H, W, stream);
+        st = note_launch(e);
+        if (st != USF_OK) return st;
+    }
+    if (gx2) {
+        cudaError_t e = vec ? launch<true, true>(x1, gout, gx2, B, C, H, W, stream)
+                            : launch<true, false>(x1, gout, gx2, B, C, H, W, stream);
+        st = note_launch(e);
+    }
+    return st;
+}
+
+}  // namespace usf

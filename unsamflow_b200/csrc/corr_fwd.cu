@@ -1,0 +1,288 @@
+// corr_fwd.cu -- cost-volume forward for sm_100a (fp32 storage, fp32 FFMA).
+//
+// Replaces: correlation_cuda.forward (models/correlation_package/correlation_cuda.cc:10-86
+// -> channels_first x2 + correlation_forward, correlation_cuda_kernel.cu:15-114), same result
+// as models/correlation_native.py:13-23:
+//     out[b,(dy+4)*9+(dx+4),y,x] = (1/C) sum_c x1[b,c,y,x] * x2[b,c,y+dy,x+dx]
+//
+// Design (one launch, no NHWC scratch, no fill, no atomics):
+//   * a CTA owns an 8x32 pixel tile; channels stream through shared memory in chunks of 8
+//     with a 3-stage cp.async (LDGSTS) ring; the x2 tile carries its 4-pixel halo, and image
+//     borders / ragged channel tails are zero-filled by cp.async src-size 0 (== F.pad zeros);
+//   * a thread owns 8 consecutive pixels of one row and the 9 dx of ONE dy: 72 fp32
+//     accumulators; per channel it issues 2 + 4 LDS.128 (x1 strip, 16-wide x2 window) for
+//     72 FFMA.  Row strides of 9 and 11 16-byte chunks make every LDS.128 phase conflict-free;
+//   * kernel A ("tile9"): 9 warps = 9 dy, every warp walks all channels (big levels);
+//   * kernel B ("splitc"): CTA = (tile, dy), 8 warps take every 8th channel and their partial
+//     tiles are summed through shared memory in a fixed order (small levels: few pixels, many
+//     channels -> 9x more CTAs, no y-halo).  Deterministic either way.
+#include "common.cuh"
+
+namespace usf {
+namespace {
+
+constexpr int TH = 8;    // tile rows
+constexpr int TW = 32;   // tile cols
+constexpr int CK = 8;    // channels per pipeline stage
+constexpr int NST = 3;   // pipeline stages
+constexpr int X1S = 36;  // x1 tile row stride in floats (9 chunks: odd -> conflict-free)
+constexpr int X2W = TW + 2 * kMaxDisp;  // 40 halo columns
+constexpr int X2S = 44;  // x2 tile row stride in floats (11 chunks)
+
+// ---------------------------------------------------------------------------
+// Stage loader.  ROWS2 = number of x2 rows staged per channel, first row = gy2_0.
+// VEC: W % 4 == 0 and 16-byte aligned bases -> every 4-float chunk is entirely
+// inside or outside the image, so one 16-byte cp.async with zero-fill does it.
+// ---------------------------------------------------------------------------
+template <int ROWS2, bool VEC, int NT>
+__device__ __forceinline__ void load_stage(float *__restrict__ st, const float *__restrict__ x1b,
+                                           const float *__restrict__ x2b, int c0, int C, int H, int W,
+                                           int y0, int x0, int gy2_0, int tid) {
+    constexpr int X1_CHUNKS = CK * TH * (TW / 4);  // 512
+    float *st2 = st + CK * TH * X1S;
+    for (int i = tid; i < X1_CHUNKS; i += NT) {
+        const int c = i >> 6, r = (i >> 3) & 7, ch = i & 7;
+        const int cc = c0 + c, gy = y0 + r, gx = x0 + 4 * ch;
+        float *dst = st + (c * TH + r) * X1S + 4 * ch;
+        const bool rowok = (cc < C) && (gy < H);
+        const float *src = x1b + ((size_t)cc * H + gy) * W + gx;
+        if (VEC) {
+            const bool ok = rowok && (gx < W);
+            cp_async16(dst, ok ? src : x1b, ok ? 16 : 0);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool ok = rowok && (gx + e < W);
+                cp_async4(dst + e, ok ? src + e : x1b, ok ? 4 : 0);
+            }
+        }
+    }
+    constexpr int X2_CHUNKS = CK * ROWS2 * (X2W / 4);
+    for (int i = tid; i < X2_CHUNKS; i += NT) {
+        const int c = i / (ROWS2 * 10);
+        const int rem = i - c * (ROWS2 * 10);
+        const int r = rem / 10, ch = rem - r * 10;
+        const int cc = c0 + c, gy = gy2_0 + r, gx = x0 - kMaxDisp + 4 * ch;
+        float *dst = st2 + (c * ROWS2 + r) * X2S + 4 * ch;
+        const bool rowok = (cc < C) && (gy >= 0) && (gy < H);
+        const float *src = x2b + ((size_t)cc * H + gy) * W + gx;
+        if (VEC) {
+            const bool ok = rowok && (gx >= 0) && (gx < W);
+            cp_async16(dst, ok ? src : x2b, ok ? 16 : 0);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool ok = rowok && (gx + e >= 0) && (gx + e < W);
+                cp_async4(dst + e, ok ? src + e : x2b, ok ? 4 : 0);
+            }
+        }
+    }
+}
+
+// 72 FFMA for one channel: acc[dx][i] += x1[i] * x2win[dx + i]
+__device__ __forceinline__ void fma_channel(float (&acc)[kD][8], const float *__restrict__ p1,
+                                            const float *__restrict__ p2) {
+    const float4 a0 = lds128(p1), a1 = lds128(p1 + 4);
+    const float4 w0 = lds128(p2), w1 = lds128(p2 + 4), w2 = lds128(p2 + 8), w3 = lds128(p2 + 12);
+    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    const float w[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
+                         w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+    for (int dx = 0; dx < kD; ++dx)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[dx][i] = fmaf(a[i], w[dx + i], acc[dx][i]);
+}
+
+__device__ __forceinline__ float finish(float v, float rc, bool leaky, float slope) {
+    v *= rc;
+    return (leaky && v < 0.f) ? v * slope : v;
+}
+
+// ---------------------------------------------------------------------------
+// Kernel A: 9 warps, warp == dy.  grid = (tiles_x, tiles_y, B)
+// ---------------------------------------------------------------------------
+constexpr int A_THREADS = 32 * kD;                       // 288
+constexpr int A_ROWS2 = TH + 2 * kMaxDisp;               // 16
+constexpr int A_STAGE = CK * TH * X1S + CK * A_ROWS2 * X2S;  // 7936 floats
+constexpr int A_SMEM = NST * A_STAGE * 4;                // 95232 B
+
+template <bool VEC>
+__global__ void __maxnreg__(112)
+corr_fwd_tile9(const float *__restrict__ x1, const float *__restrict__ x2, float *__restrict__ out, int C,
+               int H, int W, float rc, int leaky, float slope) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = lane >> 2, q = lane & 3;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+    const float *x1b = x1 + (size_t)b * C * H * W;
+    const float *x2b = x2 + (size_t)b * C * H * W;
+    const int nchunk = (C + CK - 1) / CK;
+
+    float acc[kD][8];
+#pragma unroll
+    for (int dx = 0; dx < kD; ++dx)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[dx][i] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < NST - 1; ++s) {
+        if (s < nchunk)
+            load_stage<A_ROWS2, VEC, A_THREADS>(smem + s * A_STAGE, x1b, x2b, s * CK, C, H, W, y0, x0,
+                                                y0 - kMaxDisp, tid);
+        cp_async_commit();
+    }
+    for (int k = 0; k < nchunk; ++k) {
+        cp_async_wait<NST - 2>();
+        __syncthreads();
+        const int kn = k + NST - 1;
+        if (kn < nchunk)
+            load_stage<A_ROWS2, VEC, A_THREADS>(smem + (kn % NST) * A_STAGE, x1b, x2b, kn * CK, C, H, W,
+                                                y0, x0, y0 - kMaxDisp, tid);
+        cp_async_commit();
+        const float *st = smem + (k % NST) * A_STAGE;
+        const float *p1 = st + r * X1S + 8 * q;
+        const float *p2 = st + CK * TH * X1S + (r + warp) * X2S + 8 * q;
+#pragma unroll 2
+        for (int c = 0; c < CK; ++c) fma_channel(acc, p1 + c * TH * X1S, p2 + c * A_ROWS2 * X2S);
+    }
+
+    const int gy = y0 + r, gx = x0 + 8 * q;
+    if (gy >= H) return;
+    float *o = out + (((size_t)b * kK + warp * kD) * H + gy) * W + gx;
+    const size_t kstride = (size_t)H * W;
+#pragma unroll
+    for (int dx = 0; dx < kD; ++dx, o += kstride) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = finish(acc[dx][i], rc, leaky, slope);
+        if (VEC) {
+            if (gx < W) *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
+            if (gx + 4 < W) *reinterpret_cast<float4 *>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (gx + i < W) o[i] = v[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Kernel B: CTA = (tile, b, dy); 8 warps split the channels; smem tree-less ordered sum.
+// grid = (tiles_x, tiles_y, B * 9)
+// ---------------------------------------------------------------------------
+constexpr int B_WARPS = 8;
+constexpr int B_THREADS = 32 * B_WARPS;                  // 256
+constexpr int B_STAGE = CK * TH * X1S + CK * TH * X2S;   // 5120 floats
+constexpr int B_RED = B_WARPS * kD * TH * X1S;           // 20736 floats (82944 B)
+constexpr int B_SMEM = (B_RED > NST * B_STAGE ? B_RED : NST * B_STAGE) * 4;
+
+template <bool VEC>
+__global__ void __launch_bounds__(B_THREADS, 2)
+corr_fwd_splitc(const float *__restrict__ x1, const float *__restrict__ x2, float *__restrict__ out, int C,
+                int H, int W, float rc, int leaky, float slope) {
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int r = lane >> 2, q = lane & 3;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int b = blockIdx.z / kD, dyi = blockIdx.z - b * kD;
+    const float *x1b = x1 + (size_t)b * C * H * W;
+    const float *x2b = x2 + (size_t)b * C * H * W;
+    const int nchunk = (C + CK - 1) / CK;
+    const int gy2_0 = y0 + dyi - kMaxDisp;
+
+    float acc[kD][8];
+#pragma unroll
+    for (int dx = 0; dx < kD; ++dx)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[dx][i] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < NST - 1; ++s) {
+        if (s < nchunk)
+            load_stage<TH, VEC, B_THREADS>(smem + s * B_STAGE, x1b, x2b, s * CK, C, H, W, y0, x0, gy2_0, tid);
+        cp_async_commit();
+    }
+    for (int k = 0; k < nchunk; ++k) {
+        cp_async_wait<NST - 2>();
+        __syncthreads();
+        const int kn = k + NST - 1;
+        if (kn < nchunk)
+            load_stage<TH, VEC, B_THREADS>(smem + (kn % NST) * B_STAGE, x1b, x2b, kn * CK, C, H, W, y0, x0,
+                                           gy2_0, tid);
+        cp_async_commit();
+        const float *st = smem + (k % NST) * B_STAGE;
+        // warp w takes channel w of this chunk (CK == B_WARPS)
+        fma_channel(acc, st + (warp * TH + r) * X1S + 8 * q,
+                    st + CK * TH * X1S + (warp * TH + r) * X2S + 8 * q);
+    }
+    cp_async_wait<0>();
+    __syncthreads();  // everyone is done with the stage buffers: reuse them for the reduction
+
+    float *red = smem + (size_t)warp * (kD * TH * X1S);
+#pragma unroll
+    for (int dx = 0; dx < kD; ++dx) {
+        float *p = red + (dx * TH + r) * X1S + 8 * q;
+        *reinterpret_cast<float4 *>(p) = make_float4(acc[dx][0], acc[dx][1], acc[dx][2], acc[dx][3]);
+        *reinterpret_cast<float4 *>(p + 4) = make_float4(acc[dx][4], acc[dx][5], acc[dx][6], acc[dx][7]);
+    }
+    __syncthreads();
+    // 9*8*32 = 2304 outputs, 9 per thread, x fastest -> coalesced 128-byte rows
+    float *ob = out + ((size_t)b * kK + dyi * kD) * H * W;
+#pragma unroll
+    for (int m = 0; m < kD; ++m) {
+        const int e = tid + m * B_THREADS;
+        const int dx = e >> 8, rr = (e >> 5) & 7, col = e & 31;
+        const float *p = smem + (dx * TH + rr) * X1S + col;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < B_WARPS; ++w) s += p[w * (kD * TH * X1S)];
+        const int gy = y0 + rr, gx = x0 + col;
+        if (gy < H && gx < W) ob[((size_t)dx * H + gy) * W + gx] = finish(s, rc, leaky, slope);
+    }
+}
+
+template <typename K>
+cudaError_t set_smem(K kernel, int bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+}  // namespace
+
+int corr_fwd_f32(const float *x1, const float *x2, float *out, int B, int C, int H, int W, unsigned flags,
+                 float slope, cudaStream_t stream) {
+    const bool vec = (W % 4 == 0) && (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) % 16 == 0);
+    const int tx = (W + TW - 1) / TW, ty = (H + TH - 1) / TH;
+    const float rc = 1.0f / (float)C;
+    const int leaky = (flags & USF_FLAG_LEAKY_RELU) ? 1 : 0;
+    // Few tiles and many channels: split dy over CTAs and channels over warps.
+    const long tiles = (long)tx * ty * B;
+    const bool splitc = tiles < 2 * 148 && C >= 48;
+    cudaError_t e;
+    if (splitc) {
+        dim3 grid(tx, ty, B * kD);
+        if (vec) {
+            static cudaError_t once = set_smem(corr_fwd_splitc<true>, B_SMEM);
+            (void)once;
+            corr_fwd_splitc<true><<<grid, B_THREADS, B_SMEM, stream>>>(x1, x2, out, C, H, W, rc, leaky, slope);
+        } else {
+            static cudaError_t once = set_smem(corr_fwd_splitc<false>, B_SMEM);
+            (void)once;
+            corr_fwd_splitc<false><<<grid, B_THREADS, B_SMEM, stream>>>(x1, x2, out, C, H, W, rc, leaky, slope);
+        }
+    } else {
+        dim3 grid(tx, ty, B);
+        if (vec) {
+            static cudaError_t once = set_smem(corr_fwd_tile9<true>, A_SMEM);
+            (void)once;
+            corr_fwd_tile9<true><<<grid, A_THREADS, A_SMEM, stream>>>(x1, x2, out, C, H, W, rc, leaky, slope);
+        } else {
+            static cudaError_t once = set_smem(corr_fwd_tile9<false>, A_SMEM);
+            (void)once;
+            corr_fwd_tile9<false><<<grid, A_THREADS, A_SMEM, stream>>>(x1, x2, out, C, H, W, rc, leaky, slope);
+        }
+    }
+    e = cudaGetLastError();
+    return note_launch(e);
+}
+
+}  // namespace usf

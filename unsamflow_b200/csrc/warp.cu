@@ -1,0 +1,374 @@
+// warp.cu -- flow_warp (bilinear backward warp) forward + backward for sm_100a.
+//
+// Replaces: utils/warp_utils.py:97-106 flow_warp = mesh_grid (:7-13, built on the CPU and copied
+// to the device on every call) + norm_grid (:16-23) + F.grid_sample(bilinear, align_corners=True,
+// padding border|zeros) and its autograd (ATen grid_sampler_2d_backward: fastAtomicAdd scatter).
+//
+// Coordinates are computed in registers with the reference's exact fp32 operation order
+// (no FMA contraction; SURVEY.md 7 hard part 3):
+//     v = float(i) + flow;  g = 2*v/(size-1) - 1;  ix = ((g + 1)/2) * (size-1);  [border: clip]
+//
+// Kernels (HBM/L2-bound gathers; one thread = one pixel x one channel slice, pixels consecutive
+// across a warp so every access is coalesced or near-coalesced):
+//   warp_fwd_kernel     4 predicated tap loads + 1 store per channel.
+//   warp_bwd_kernel     g_flow: per-slice partial sums over channels, fixed-order reduction through
+//                       shared memory.  Optionally (a) emits the tap lists used by the atomic-free
+//                       g_x gather below, or (b) scatters g_x with red.global.add.f32 (A/B mode).
+//   warp_gx_gather      atomic-free g_x: every TARGET pixel owns a list of (source pixel, weight)
+//                       pairs (built once per call, channel independent, sorted by source so the
+//                       sum order is deterministic) and gathers  g_x[c,t] = sum_i w_i * gO[c,src_i]
+//                       with plain loads and one plain store: no float atomics, no zero-fill.
+//   warp_gx_overflow    targets hit by more than kSlots taps (e.g. a region clipped onto the image
+//                       border) keep their first kSlots taps in the list; the rest go through a
+//                       side list handled with float atomics after the gather has written g_x.
+#include "common.cuh"
+
+namespace usf {
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kSlots = 8;  // list capacity per target pixel
+
+struct Taps {
+    int o_nw, o_ne, o_sw, o_se;      // offsets inside one H*W plane (valid only if ok_*)
+    bool k_nw, k_ne, k_sw, k_se;     // tap inside the image
+    float ex, wx, ey, wy;            // 1-D weights: ex = x1 - ix, wx = ix - x0, ...
+    float mx, my;                    // d(ix)/d(grid) multipliers incl. border clip gradient
+};
+
+// One axis of the reference's coordinate pipeline.  rcp: ATen-CUDA flavour of `/ (size-1)`.
+__device__ __forceinline__ float src_coord(int i, float fl, int size, bool border, bool rcp, float &mult) {
+    const float sz = (float)(size - 1);
+    const float v = __fadd_rn((float)i, fl);
+    const float t = __fmul_rn(2.0f, v);
+    const float qn = rcp ? __fmul_rn(t, __fdiv_rn(1.0f, sz)) : __fdiv_rn(t, sz);
+    const float g = __fsub_rn(qn, 1.0f);
+    const float h = __fmul_rn(__fadd_rn(g, 1.0f), 0.5f);
+    float ix = __fmul_rn(h, sz);
+    mult = __fmul_rn(sz, 0.5f);
+    if (border) {
+        if (ix <= 0.f) { ix = 0.f; mult = 0.f; }
+        else if (ix >= sz) { ix = sz; mult = 0.f; }
+    }
+    return ix;
+}
+
+__device__ __forceinline__ Taps make_taps(int y, int xo, float u, float v, int H, int W, bool border,
+                                          bool rcp) {
+    Taps t;
+    const float ix = src_coord(xo, u, W, border, rcp, t.mx);
+    const float iy = src_coord(y, v, H, border, rcp, t.my);
+    // floorf on +-inf / NaN: the int conversions saturate and every tap is out of range
+    const float fx = floorf(ix), fy = floorf(iy);
+    t.ex = __fsub_rn(__fadd_rn(fx, 1.0f), ix);
+    t.wx = __fsub_rn(ix, fx);
+    t.ey = __fsub_rn(__fadd_rn(fy, 1.0f), iy);
+    t.wy = __fsub_rn(iy, fy);
+    // clamp before the int conversion so huge flows cannot overflow the offset arithmetic
+    const int x0 = (int)fminf(fmaxf(fx, -2.0f), (float)W);
+    const int y0 = (int)fminf(fmaxf(fy, -2.0f), (float)H);
+    const int x1 = x0 + 1, y1 = y0 + 1;
+    const bool xa = (x0 >= 0) && (x0 < W), xb = (x1 >= 0) && (x1 < W);
+    const bool ya = (y0 >= 0) && (y0 < H), yb = (y1 >= 0) && (y1 < H);
+    const bool fin = (ix == ix) && (iy == iy);  // NaN coordinates sample nothing
+    t.k_nw = xa && ya && fin; t.k_ne = xb && ya && fin; t.k_sw = xa && yb && fin; t.k_se = xb && yb && fin;
+    t.o_nw = y0 * W + x0; t.o_ne = t.o_nw + 1; t.o_sw = t.o_nw + W; t.o_se = t.o_sw + 1;
+    return t;
+}
+
+__device__ __forceinline__ float ldp(const float *__restrict__ base, int off, bool ok) {
+    return ok ? __ldg(base + off) : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int NS>
+__global__ void __launch_bounds__(kBlock)
+warp_fwd_kernel(const float *__restrict__ x, const float *__restrict__ flow, float *__restrict__ out, int N,
+                int C, int H, int W, int border, int rcp) {
+    constexpr int PPB = kBlock / NS;
+    const int p = blockIdx.x * PPB + (threadIdx.x % PPB);
+    const int cs = threadIdx.x / PPB;
+    if (p >= N) return;
+    const int HW = H * W;
+    const int b = p / HW, rem = p - b * HW;
+    const int y = rem / W, xo = rem - y * W;
+    const float u = __ldg(flow + (size_t)b * 2 * HW + rem);
+    const float v = __ldg(flow + (size_t)b * 2 * HW + HW + rem);
+    const Taps t = make_taps(y, xo, u, v, H, W, border, rcp);
+    const float nw = t.ex * t.ey, ne = t.wx * t.ey, sw = t.ex * t.wy, se = t.wx * t.wy;
+    const float *xb = x + (size_t)b * C * HW;
+    float *ob = out + (size_t)b * C * HW + rem;
+#pragma unroll 4
+    for (int c = cs; c < C; c += NS) {
+        const float *pl = xb + (size_t)c * HW;
+        float acc = ldp(pl, t.o_nw, t.k_nw) * nw;
+        acc = fmaf(ldp(pl, t.o_ne, t.k_ne), ne, acc);
+        acc = fmaf(ldp(pl, t.o_sw, t.k_sw), sw, acc);
+        acc = fmaf(ldp(pl, t.o_se, t.k_se), se, acc);
+        ob[(size_t)c * HW] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Workspace of the atomic-free g_x path, N = B*H*W target pixels:
+//   int   cnt[N]            taps received per target (zeroed by a memset node each call)
+//   int   ovf_n[4]          number of overflow taps (+ padding to 16 bytes)
+//   int2  ent[N][kSlots]    (source pixel inside its image plane, weight bits)
+//   int   ovf_tgt[4N], ovf_src[4N]; float ovf_w[4N]     overflow side list (worst case: every tap)
+struct Workspace {
+    int *cnt;
+    int *ovf_n;
+    int2 *ent;
+    int *ovf_tgt;
+    int *ovf_src;
+    float *ovf_w;
+};
+__host__ __device__ inline size_t ws_bytes(size_t N) {
+    return N * 4 + 16 + N * kSlots * 8 + 3 * (4 * N) * 4;
+}
+inline Workspace carve(void *base, size_t N) {
+    char *p = (char *)base;
+    Workspace w;
+    w.cnt = (int *)p;               p += N * 4;
+    w.ovf_n = (int *)p;             p += 16;
+    w.ent = (int2 *)p;              p += N * kSlots * 8;
+    w.ovf_tgt = (int *)p;           p += 4 * N * 4;
+    w.ovf_src = (int *)p;           p += 4 * N * 4;
+    w.ovf_w = (float *)p;
+    return w;
+}
+
+__device__ __forceinline__ void emit_tap(const Workspace &ws, int plane0, int off, bool ok, float w,
+                                         int src) {
+    if (!ok || w == 0.f) return;
+    const int tgt = plane0 + off;
+    const int slot = atomicAdd(ws.cnt + tgt, 1);  // integer bookkeeping only; sums stay atomic-free
+    if (slot < kSlots) {
+        ws.ent[(size_t)tgt * kSlots + slot] = make_int2(src, __float_as_int(w));
+    } else {
+        const int j = atomicAdd(ws.ovf_n, 1);
+        ws.ovf_tgt[j] = tgt;
+        ws.ovf_src[j] = src;
+        ws.ovf_w[j] = w;
+    }
+}
+
+// MODE 0: g_flow only.  MODE 1: (g_flow) + emit tap lists.  MODE 2: (g_flow) + atomic g_x scatter.
+template <int NS, int MODE>
+__global__ void __launch_bounds__(kBlock)
+warp_bwd_kernel(const float *__restrict__ x, const float *__restrict__ flow, const float *__restrict__ gout,
+                float *__restrict__ gx, float *__restrict__ gflow, Workspace ws, int N, int C, int H, int W,
+                int border, int rcp) {
+    constexpr int PPB = kBlock / NS;
+    __shared__ float red[2][NS][PPB];
+    const int pl = threadIdx.x % PPB;
+    const int p = blockIdx.x * PPB + pl;
+    const int cs = threadIdx.x / PPB;
+    const bool live = p < N;
+    const int HW = H * W;
+    float gix = 0.f, giy = 0.f;
+    int b = 0, rem = 0;
+    Taps t;
+    if (live) {
+        b = p / HW;
+        rem = p - b * HW;
+        const int y = rem / W, xo = rem - y * W;
+        const float u = __ldg(flow + (size_t)b * 2 * HW + rem);
+        const float v = __ldg(flow + (size_t)b * 2 * HW + HW + rem);
+        t = make_taps(y, xo, u, v, H, W, border, rcp);
+        const float nw = t.ex * t.ey, ne = t.wx * t.ey, sw = t.ex * t.wy, se = t.wx * t.wy;
+        if (MODE == 1 && cs == 0) {
+            emit_tap(ws, b * HW, t.o_nw, t.k_nw, nw, rem);
+            emit_tap(ws, b * HW, t.o_ne, t.k_ne, ne, rem);
+            emit_tap(ws, b * HW, t.o_sw, t.k_sw, sw, rem);
+            emit_tap(ws, b * HW, t.o_se, t.k_se, se, rem);
+        }
+        const float *xb = x + (size_t)b * C * HW;
+        const float *gb = gout + (size_t)b * C * HW + rem;
+        float *gxb = (MODE == 2) ? gx + (size_t)b * C * HW : nullptr;
+        if (gflow != nullptr || MODE == 2) {
+#pragma unroll 4
+            for (int c = cs; c < C; c += NS) {
+                const float go = __ldg(gb + (size_t)c * HW);
+                if (gflow != nullptr) {
+                    const float *plane = xb + (size_t)c * HW;
+                    const float vnw = ldp(plane, t.o_nw, t.k_nw), vne = ldp(plane, t.o_ne, t.k_ne);
+                    const float vsw = ldp(plane, t.o_sw, t.k_sw), vse = ldp(plane, t.o_se, t.k_se);
+                    gix = fmaf(go, fmaf(t.ey, vne - vnw, t.wy * (vse - vsw)), gix);
+                    giy = fmaf(go, fmaf(t.ex, vsw - vnw, t.wx * (vse - vne)), giy);
+                }
+                if (MODE == 2) {
+                    float *plane = gxb + (size_t)c * HW;
+                    if (t.k_nw) atomicAdd(plane + t.o_nw, nw * go);
+                    if (t.k_ne) atomicAdd(plane + t.o_ne, ne * go);
+                    if (t.k_sw) atomicAdd(plane + t.o_sw, sw * go);
+                    if (t.k_se) atomicAdd(plane + t.o_se, se * go);
+                }
+            }
+        }
+    }
+    if (gflow == nullptr) return;
+    if (NS > 1) {
+        red[0][cs][pl] = gix;
+        red[1][cs][pl] = giy;
+        __syncthreads();
+        if (cs != 0 || !live) return;
+        gix = red[0][0][pl];
+        giy = red[1][0][pl];
+#pragma unroll
+        for (int s = 1; s < NS; ++s) {
+            gix += red[0][s][pl];
+            giy += red[1][s][pl];
+        }
+    } else if (!live) {
+        return;
+    }
+    // grid_sampler backward: ggrid = mult * gi; norm_grid backward: (g / (size-1)) * 2
+    const float sx = (float)(W - 1), sy = (float)(H - 1);
+    const float gxn = __fmul_rn(t.mx, gix), gyn = __fmul_rn(t.my, giy);
+    const float dfx = rcp ? __fmul_rn(gxn, __fdiv_rn(1.0f, sx)) : __fdiv_rn(gxn, sx);
+    const float dfy = rcp ? __fmul_rn(gyn, __fdiv_rn(1.0f, sy)) : __fdiv_rn(gyn, sy);
+    gflow[(size_t)b * 2 * HW + rem] = __fmul_rn(dfx, 2.0f);
+    gflow[(size_t)b * 2 * HW + HW + rem] = __fmul_rn(dfy, 2.0f);
+}
+
+__device__ __forceinline__ void cswap(int &ka, float &wa, int &kb, float &wb) {
+    if (kb < ka) {
+        const int tk = ka; ka = kb; kb = tk;
+        const float tw = wa; wa = wb; wb = tw;
+    }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(kBlock)
+warp_gx_gather(const float *__restrict__ gout, float *__restrict__ gx, Workspace ws, int N, int C, int HW) {
+    constexpr int PPB = kBlock / NS;
+    const int p = blockIdx.x * PPB + (threadIdx.x % PPB);
+    const int cs = threadIdx.x / PPB;
+    if (p >= N) return;
+    const int b = p / HW, rem = p - b * HW;
+    const int n = min(ws.cnt[p], kSlots);
+    int src[kSlots];
+    float w[kSlots];
+    const int4 *e4 = reinterpret_cast<const int4 *>(ws.ent + (size_t)p * kSlots);
+#pragma unroll
+    for (int i = 0; i < kSlots / 2; ++i) {
+        int4 e = make_int4(0, 0, 0, 0);
+        if (2 * i < n) e = e4[i];
+        src[2 * i] = (2 * i < n) ? e.x : 0x7fffffff;
+        w[2 * i] = (2 * i < n) ? __int_as_float(e.y) : 0.f;
+        src[2 * i + 1] = (2 * i + 1 < n) ? e.z : 0x7fffffff;
+        w[2 * i + 1] = (2 * i + 1 < n) ? __int_as_float(e.w) : 0.f;
+    }
+    // 19-comparator sorting network for 8 keys: list order no longer depends on atomic timing
+#define USF_CS(a, b) cswap(src[a], w[a], src[b], w[b])
+    USF_CS(0, 1); USF_CS(2, 3); USF_CS(4, 5); USF_CS(6, 7);
+    USF_CS(0, 2); USF_CS(1, 3); USF_CS(4, 6); USF_CS(5, 7);
+    USF_CS(1, 2); USF_CS(5, 6); USF_CS(0, 4); USF_CS(3, 7);
+    USF_CS(1, 5); USF_CS(2, 6);
+    USF_CS(1, 4); USF_CS(3, 6);
+    USF_CS(2, 4); USF_CS(3, 5);
+    USF_CS(3, 4);
+#undef USF_CS
+    const float *gb = gout + (size_t)b * C * HW;
+    float *ob = gx + (size_t)b * C * HW + rem;
+#pragma unroll 2
+    for (int c = cs; c < C; c += NS) {
+        const float *plane = gb + (size_t)c * HW;
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < kSlots; ++i)
+            if (i < n) acc = fmaf(w[i], __ldg(plane + src[i]), acc);
+        ob[(size_t)c * HW] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+warp_gx_overflow(const float *__restrict__ gout, float *__restrict__ gx, Workspace ws, int cap, int C, int HW) {
+    const int n = min(ws.ovf_n[0], cap);
+    const long total = (long)n * C;
+    for (long it = (long)blockIdx.x * kBlock + threadIdx.x; it < total; it += (long)gridDim.x * kBlock) {
+        const int c = (int)(it / n), j = (int)(it - (long)c * n);
+        const int tgt = ws.ovf_tgt[j];
+        const int b = tgt / HW, trem = tgt - b * HW;
+        const size_t plane = ((size_t)b * C + c) * HW;
+        atomicAdd(gx + plane + trem, ws.ovf_w[j] * __ldg(gout + plane + ws.ovf_src[j]));
+    }
+}
+
+int pick_ns(int C) { return C >= 32 ? 8 : C >= 16 ? 4 : C >= 8 ? 2 : 1; }
+
+}  // namespace
+
+size_t warp_bwd_workspace_bytes(size_t N) { return ws_bytes(N); }
+
+int warp_fwd_f32(const float *x, const float *flow, float *out, int B, int C, int H, int W, int pad_mode,
+                 unsigned flags, cudaStream_t stream) {
+    const int N = B * H * W;
+    const int border = pad_mode == USF_PAD_BORDER, rcp = (flags & USF_FLAG_COORD_RECIPROCAL) ? 1 : 0;
+    const int ns = pick_ns(C);
+    const int blocks = (N + kBlock / ns - 1) / (kBlock / ns);
+#define USF_LAUNCH(NS) warp_fwd_kernel<NS><<<blocks, kBlock, 0, stream>>>(x, flow, out, N, C, H, W, border, rcp)
+    switch (ns) {
+        case 8: USF_LAUNCH(8); break;
+        case 4: USF_LAUNCH(4); break;
+        case 2: USF_LAUNCH(2); break;
+        default: USF_LAUNCH(1); break;
+    }
+#undef USF_LAUNCH
+    return note_launch(cudaGetLastError());
+}
+
+template <int MODE>
+static cudaError_t launch_bwd(int ns, int blocks, const float *x, const float *flow, const float *gout,
+                              float *gx, float *gflow, Workspace ws, int N, int C, int H, int W, int border,
+                              int rcp, cudaStream_t stream) {
+#define USF_LAUNCH(NS) \
+    warp_bwd_kernel<NS, MODE><<<blocks, kBlock, 0, stream>>>(x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp)
+    switch (ns) {
+        case 8: USF_LAUNCH(8); break;
+        case 4: USF_LAUNCH(4); break;
+        case 2: USF_LAUNCH(2); break;
+        default: USF_LAUNCH(1); break;
+    }
+#undef USF_LAUNCH
+    return cudaGetLastError();
+}
+
+int warp_bwd_f32(const float *x, const float *flow, const float *gout, float *gx, float *gflow, int B, int C,
+                 int H, int W, int pad_mode, unsigned flags, void *workspace, size_t workspace_bytes,
+                 cudaStream_t stream) {
+    const int N = B * H * W, HW = H * W;
+    const int border = pad_mode == USF_PAD_BORDER, rcp = (flags & USF_FLAG_COORD_RECIPROCAL) ? 1 : 0;
+    const int ns = pick_ns(C);
+    const int blocks = (N + kBlock / ns - 1) / (kBlock / ns);
+    Workspace ws = {};
+    if (gx == nullptr) {
+        return note_launch(launch_bwd<0>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
+    }
+    if (flags & USF_FLAG_WARP_BWD_ATOMIC) {
+        cudaError_t e = cudaMemsetAsync(gx, 0, (size_t)N * C * sizeof(float), stream);
+        if (e != cudaSuccess) { note_cuda_error(e); return USF_ERR_CUDA; }
+        return note_launch(launch_bwd<2>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
+    }
+    if (workspace == nullptr || workspace_bytes < ws_bytes((size_t)N)) return USF_ERR_WORKSPACE;
+    ws = carve(workspace, (size_t)N);
+    cudaError_t e = cudaMemsetAsync(ws.cnt, 0, (size_t)N * 4 + 16, stream);
+    if (e != cudaSuccess) { note_cuda_error(e); return USF_ERR_CUDA; }
+    int st = note_launch(launch_bwd<1>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
+    if (st != USF_OK) return st;
+#define USF_LAUNCH(NS) warp_gx_gather<NS><<<blocks, kBlock, 0, stream>>>(gout, gx, ws, N, C, HW)
+    switch (ns) {
+        case 8: USF_LAUNCH(8); break;
+        case 4: USF_LAUNCH(4); break;
+        case 2: USF_LAUNCH(2); break;
+        default: USF_LAUNCH(1); break;
+    }
+#undef USF_LAUNCH
+    st = note_launch(cudaGetLastError());
+    if (st != USF_OK) return st;
+    warp_gx_overflow<<<148, kBlock, 0, stream>>>(gout, gx, ws, 4 * N, C, HW);
+    return note_launch(cudaGetLastError());
+}
+
+}  // namespace usf

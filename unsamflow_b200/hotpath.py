@@ -1,0 +1,199 @@
+"""The PWC-Lite hot path as a schedulable unit: shapes, byte accounting and one "step".
+
+A *step* is every Correlation / flow_warp call one PWC-Lite training iteration issues, forward
+and backward, on one batch of synthetic pairs (verified call counts):
+
+  model, per direction (flows_12 and flows_21, models/pwclite.py:430-432), decoder levels 0..4
+  (C = 192,128,96,64,32):
+      level > 0:  x2_warp = flow_warp(x2, flow)           pwclite.py:302   (grads to x2 AND flow)
+      every lvl:  out     = Correlation(x1, x2_warp)      pwclite.py:307   (grads to both)
+  loss, per direction, the 4 photometric scales (losses/flow_loss.py:126-131):
+      im_recons = flow_warp(im_scaled, flow, pad=border)  C = 3, gradient wrt FLOW only
+
+  -> 10 corr fwd + 10 corr bwd + 16 warp fwd + 16 warp bwd per step (kitti_base / sintel_base).
+
+Everything is preallocated, so a step enqueues kernels only (CUDA-graph capturable).  The convs,
+flow estimators and loss arithmetic around these calls are cuDNN / elementwise PyTorch in the
+reference and are out of scope here; upstream gradients are synthetic.
+"""
+from dataclasses import dataclass, field
+
+import torch
+
+from . import ops
+
+DECODER_CHANNELS = (192, 128, 96, 64, 32)  # models/pwclite.py:183 reversed, levels 0..4
+NUM_LOSS_SCALES = 4                        # w_ph_scales [1,1,1,1,0], configs/kitti_base.json
+K = ops.NUM_DISPLACEMENTS
+
+
+def conv_out(n):
+    """3x3 stride-2 pad-1 conv output size (models/pwclite.py:59-63)."""
+    return (n - 1) // 2 + 1
+
+
+def pyramid_shapes(H, W):
+    """[(C, h, w)] for decoder levels 0..4 of an H x W input (SURVEY.md 8 header)."""
+    sizes = []
+    h, w = H, W
+    for _ in range(6):
+        h, w = conv_out(h), conv_out(w)
+        sizes.append((h, w))
+    # feature pyramid is reversed: level 0 = coarsest (6th conv), level 4 = 2nd conv
+    return [(c,) + sizes[5 - lvl] for lvl, c in enumerate(DECODER_CHANNELS)]
+
+
+def loss_shapes(H, W):
+    """[(3, h, w)] for the photometric scales: flows at 1, 1/2, 1/4, 1/8 resolution
+    (PWCLite outputs 256x832 .. 32x104 for KITTI; flow_loss.py:128-131 resizes the images)."""
+    return [(3, H >> s, W >> s) for s in range(NUM_LOSS_SCALES)]
+
+
+# ---- algorithmic bytes / flops (s = 4 bytes, flow always fp32) -------------------
+def corr_fwd_bytes(B, C, H, W):
+    return (2 * C + K) * 4 * B * H * W
+
+
+def corr_bwd_bytes(B, C, H, W):
+    return (K + 4 * C) * 4 * B * H * W
+
+
+def corr_fwd_flops(B, C, H, W):
+    return 2 * K * C * B * H * W
+
+
+def warp_fwd_bytes(B, C, H, W):
+    return (2 * C * 4 + 8) * B * H * W
+
+
+def warp_bwd_bytes(B, C, H, W, need_gx=True):
+    return ((3 if need_gx else 2) * C * 4 + 16) * B * H * W
+
+
+@dataclass
+class OpRecord:
+    name: str      # e.g. "corr_bwd.L4.d12"
+    kind: str      # corr_fwd | corr_bwd | warp_fwd | warp_bwd | warp_bwd_flow
+    fn: object
+    bytes: int
+    flops: int = 0
+    launches: int = 1
+    shape: tuple = field(default_factory=tuple)
+
+
+class HotPathStep:
+    """Preallocated synthetic inputs/outputs + the ordered op list of one training step."""
+
+    def __init__(self, B, H, W, device="cuda", seed=42, flow_sigma=3.0, pad="border"):
+        self.B, self.H, self.W, self.pad = B, H, W, pad
+        self.device = torch.device(device)
+        gen = torch.Generator(device="cpu").manual_seed(seed)
+
+        def randn(*shape, scale=1.0):
+            return (torch.randn(*shape, generator=gen) * scale).to(self.device)
+
+        self.levels = pyramid_shapes(H, W)
+        self.scales = loss_shapes(H, W)
+        t = self.t = {}          # every tensor, by name
+        self.input_names = []    # tensors a caller would have to supply (for the e2e H2D leg)
+        for lvl, (C, h, w) in enumerate(self.levels):
+            for n in ("f1", "f2"):
+                t[f"{n}.L{lvl}"] = randn(B, C, h, w)
+                self.input_names.append(f"{n}.L{lvl}")
+            for d in ("d12", "d21"):
+                if lvl > 0:
+                    t[f"flow.L{lvl}.{d}"] = randn(B, 2, h, w, scale=flow_sigma)
+                    t[f"x2w.L{lvl}.{d}"] = torch.empty(B, C, h, w, device=self.device)
+                    t[f"gfeat2.L{lvl}.{d}"] = torch.empty(B, C, h, w, device=self.device)
+                    t[f"gflow.L{lvl}.{d}"] = torch.empty(B, 2, h, w, device=self.device)
+                    t[f"ws.L{lvl}.{d}"] = torch.empty(
+                        ops.warp_bwd_workspace_bytes(t[f"f1.L{lvl}"]), dtype=torch.uint8, device=self.device)
+                    self.input_names.append(f"flow.L{lvl}.{d}")
+                t[f"corr.L{lvl}.{d}"] = torch.empty(B, K, h, w, device=self.device)
+                t[f"gcorr.L{lvl}.{d}"] = randn(B, K, h, w)
+                t[f"gx1.L{lvl}.{d}"] = torch.empty(B, C, h, w, device=self.device)
+                t[f"gx2.L{lvl}.{d}"] = torch.empty(B, C, h, w, device=self.device)
+                self.input_names.append(f"gcorr.L{lvl}.{d}")
+        for s, (C, h, w) in enumerate(self.scales):
+            for n in ("im1", "im2"):
+                t[f"{n}.S{s}"] = torch.rand(B, C, h, w, generator=gen).to(self.device)
+                self.input_names.append(f"{n}.S{s}")
+            for d in ("d12", "d21"):
+                t[f"lflow.S{s}.{d}"] = randn(B, 2, h, w, scale=flow_sigma)
+                t[f"recons.S{s}.{d}"] = torch.empty(B, C, h, w, device=self.device)
+                t[f"grecons.S{s}.{d}"] = randn(B, C, h, w)
+                t[f"glflow.S{s}.{d}"] = torch.empty(B, 2, h, w, device=self.device)
+                self.input_names += [f"lflow.S{s}.{d}", f"grecons.S{s}.{d}"]
+        self.ops = self._build_ops()
+
+    # -- schedule -------------------------------------------------------------------------------
+    def _build_ops(self):
+        t, B, pad = self.t, self.B, self.pad
+        fwd, bwd = [], []
+        for d in ("d12", "d21"):
+            a, b = ("f1", "f2") if d == "d12" else ("f2", "f1")
+            for lvl, (C, h, w) in enumerate(self.levels):
+                x1, x2 = t[f"{a}.L{lvl}"], t[f"{b}.L{lvl}"]
+                shp = (B, C, h, w)
+                if lvl > 0:
+                    fl, x2w = t[f"flow.L{lvl}.{d}"], t[f"x2w.L{lvl}.{d}"]
+                    fwd.append(OpRecord(f"warp_fwd.L{lvl}.{d}", "warp_fwd",
+                                        (lambda x2=x2, fl=fl, x2w=x2w: ops.warp_fwd(x2, fl, pad, out=x2w)),
+                                        warp_fwd_bytes(*shp), shape=shp))
+                else:
+                    x2w = x2
+                out, go = t[f"corr.L{lvl}.{d}"], t[f"gcorr.L{lvl}.{d}"]
+                g1, g2 = t[f"gx1.L{lvl}.{d}"], t[f"gx2.L{lvl}.{d}"]
+                fwd.append(OpRecord(f"corr_fwd.L{lvl}.{d}", "corr_fwd",
+                                    (lambda x1=x1, x2w=x2w, out=out: ops.corr_fwd(x1, x2w, out=out)),
+                                    corr_fwd_bytes(*shp), corr_fwd_flops(*shp), shape=shp))
+                # appended in reverse of execution order: the list is flipped below
+                if lvl > 0:
+                    gf2, gfl, ws = t[f"gfeat2.L{lvl}.{d}"], t[f"gflow.L{lvl}.{d}"], t[f"ws.L{lvl}.{d}"]
+                    bwd.append(OpRecord(f"warp_bwd.L{lvl}.{d}", "warp_bwd",
+                                        (lambda x2=x2, fl=fl, g2=g2, gf2=gf2, gfl=gfl, ws=ws:
+                                         ops.warp_bwd(x2, fl, g2, pad, gx=gf2, gflow=gfl, workspace=ws)),
+                                        warp_bwd_bytes(*shp), launches=3, shape=shp))
+                bwd.append(OpRecord(f"corr_bwd.L{lvl}.{d}", "corr_bwd",
+                                    (lambda x1=x1, x2w=x2w, go=go, g1=g1, g2=g2:
+                                     ops.corr_bwd(x1, x2w, go, gx1=g1, gx2=g2)),
+                                    corr_bwd_bytes(*shp), 2 * corr_fwd_flops(*shp), launches=2, shape=shp))
+            im = "im2" if d == "d12" else "im1"
+            for s, (C, h, w) in enumerate(self.scales):
+                x, fl = t[f"{im}.S{s}"], t[f"lflow.S{s}.{d}"]
+                rec, gr, gfl = t[f"recons.S{s}.{d}"], t[f"grecons.S{s}.{d}"], t[f"glflow.S{s}.{d}"]
+                shp = (B, C, h, w)
+                fwd.append(OpRecord(f"lwarp_fwd.S{s}.{d}", "warp_fwd",
+                                    (lambda x=x, fl=fl, rec=rec: ops.warp_fwd(x, fl, pad, out=rec)),
+                                    warp_fwd_bytes(*shp), shape=shp))
+                bwd.append(OpRecord(f"lwarp_bwd.S{s}.{d}", "warp_bwd_flow",
+                                    (lambda x=x, fl=fl, gr=gr, gfl=gfl:
+                                     ops.warp_bwd(x, fl, gr, pad, need_gx=False, gflow=gfl)),
+                                    warp_bwd_bytes(*shp, need_gx=False), shape=shp))
+        # backward runs after the whole forward, finest level first (autograd order)
+        return fwd + bwd[::-1]
+
+    # -- execution ------------------------------------------------------------------------------
+    def run(self, ops_subset=None):
+        for op in (self.ops if ops_subset is None else ops_subset):
+            op.fn()
+
+    @property
+    def launches_per_step(self):
+        return sum(op.launches for op in self.ops)
+
+    @property
+    def bytes_per_step(self):
+        return sum(op.bytes for op in self.ops)
+
+    @property
+    def flops_per_step(self):
+        return sum(op.flops for op in self.ops)
+
+    def input_bytes(self):
+        return sum(self.t[n].numel() * self.t[n].element_size() for n in self.input_names)
+
+    def result_names(self):
+        """What a caller reads back: gradients at the finest model level and loss scale."""
+        top = len(self.levels) - 1
+        return [f"gx1.L{top}.d12", f"gflow.L{top}.d12", "glflow.S0.d12", "glflow.S0.d21"]

@@ -1,0 +1,152 @@
+"""Raw (no autograd) tensor front end of the C ABI: validation + pointer extraction only.
+
+Mirrors what the reference's C++ host layer does (models/correlation_package/
+correlation_cuda.cc:10-86, 88-165: shape math, output allocation, stream lookup), minus the
+scratch tensors and fills the new kernels do not need.
+"""
+import torch
+
+from . import _lib
+
+_PADS = {"border": _lib.PAD_BORDER, "zeros": _lib.PAD_ZEROS}
+MAX_DISPLACEMENT = 4
+NUM_DISPLACEMENTS = 81
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _feat(t, name):
+    if not isinstance(t, torch.Tensor) or t.dim() != 4:
+        raise ValueError(f"{name}: expected a 4-D tensor [B,C,H,W]")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: unsamflow_b200 runs on CUDA tensors only (got {t.device}); "
+                           "there is no CPU path")
+    if t.dtype != torch.float32:
+        raise NotImplementedError(f"{name}: dtype {t.dtype} is not supported yet (float32 only)")
+    return t.contiguous()
+
+
+def _same(a, b, na, nb):
+    if a.shape != b.shape:
+        raise ValueError(f"{na}.shape {tuple(a.shape)} != {nb}.shape {tuple(b.shape)}")
+    if a.device != b.device:
+        raise RuntimeError(f"{na} and {nb} are on different devices")
+
+
+def _flags(leaky=False, reciprocal=False, atomic=False):
+    return ((_lib.FLAG_LEAKY_RELU if leaky else 0) | (_lib.FLAG_COORD_RECIPROCAL if reciprocal else 0)
+            | (_lib.FLAG_WARP_BWD_ATOMIC if atomic else 0))
+
+
+def corr_fwd(x1, x2, leaky_slope=None, out=None):
+    """[B,C,H,W] x2 -> [B,81,H,W]; optional fused LeakyReLU(leaky_slope)."""
+    L = _lib.load()
+    x1, x2 = _feat(x1, "x1"), _feat(x2, "x2")
+    _same(x1, x2, "x1", "x2")
+    B, C, H, W = x1.shape
+    if out is None:
+        out = torch.empty((B, NUM_DISPLACEMENTS, H, W), dtype=x1.dtype, device=x1.device)
+    with torch.cuda.device(x1.device):
+        st = L.usf_corr_fwd(x1.data_ptr(), x2.data_ptr(), out.data_ptr(), B, C, H, W, MAX_DISPLACEMENT,
+                            _lib.F32, _flags(leaky=leaky_slope is not None),
+                            float(leaky_slope or 0.0), _stream(x1))
+    _lib.check(st, "usf_corr_fwd")
+    return out
+
+
+def corr_bwd(x1, x2, gout, need_gx1=True, need_gx2=True, gx1=None, gx2=None):
+    """-> (gx1, gx2); pass preallocated gx1= / gx2= to avoid allocations (CUDA-graph friendly)."""
+    L = _lib.load()
+    x1, x2, gout = _feat(x1, "x1"), _feat(x2, "x2"), _feat(gout, "grad_output")
+    _same(x1, x2, "x1", "x2")
+    B, C, H, W = x1.shape
+    if tuple(gout.shape) != (B, NUM_DISPLACEMENTS, H, W):
+        raise ValueError(f"grad_output.shape {tuple(gout.shape)} != {(B, NUM_DISPLACEMENTS, H, W)}")
+    if need_gx1 and gx1 is None:
+        gx1 = torch.empty_like(x1)
+    if need_gx2 and gx2 is None:
+        gx2 = torch.empty_like(x2)
+    with torch.cuda.device(x1.device):
+        st = L.usf_corr_bwd(x1.data_ptr(), x2.data_ptr(), gout.data_ptr(),
+                            gx1.data_ptr() if need_gx1 else None, gx2.data_ptr() if need_gx2 else None,
+                            B, C, H, W, MAX_DISPLACEMENT, _lib.F32, 0, _stream(x1))
+    _lib.check(st, "usf_corr_bwd")
+    return gx1, gx2
+
+
+def _flow(flow, x):
+    if not isinstance(flow, torch.Tensor) or flow.dim() != 4:
+        raise ValueError("flow12: expected a 4-D tensor [B,2,H,W]")
+    B, _, H, W = x.shape
+    if tuple(flow.shape) != (B, 2, H, W):
+        raise ValueError(f"flow12.shape {tuple(flow.shape)} != {(B, 2, H, W)}")
+    if flow.device != x.device:
+        raise RuntimeError("x and flow12 are on different devices")
+    return flow.float().contiguous()
+
+
+def _pad(pad):
+    try:
+        return _PADS[pad]
+    except KeyError:
+        raise ValueError(f"pad={pad!r}: expected 'border' or 'zeros'") from None
+
+
+def warp_fwd(x, flow, pad="border", reciprocal=False, out=None):
+    L = _lib.load()
+    x = _feat(x, "x")
+    flow = _flow(flow, x)
+    B, C, H, W = x.shape
+    if H < 2 or W < 2:
+        raise ValueError("flow_warp needs H, W >= 2 (the reference divides by size-1)")
+    if out is None:
+        out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        st = L.usf_warp_fwd(x.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, H, W, _pad(pad), _lib.F32,
+                            _flags(reciprocal=reciprocal), _stream(x))
+    _lib.check(st, "usf_warp_fwd")
+    return out
+
+
+def warp_bwd_workspace_bytes(x, atomic=False):
+    B, C, H, W = x.shape
+    return int(_lib.load().usf_warp_bwd_workspace_bytes(B, C, H, W, _flags(atomic=atomic)))
+
+
+def warp_bwd(x, flow, gout, pad="border", need_gx=True, need_gflow=True, reciprocal=False, atomic=False,
+             gx=None, gflow=None, workspace=None):
+    """-> (gx, gflow); gx= / gflow= / workspace= (uint8 tensor) may be preallocated."""
+    L = _lib.load()
+    x, gout = _feat(x, "x"), _feat(gout, "grad_output")
+    _same(x, gout, "x", "grad_output")
+    flow = _flow(flow, x)
+    B, C, H, W = x.shape
+    flags = _flags(reciprocal=reciprocal, atomic=atomic)
+    if need_gx and gx is None:
+        gx = torch.empty_like(x)
+    if need_gflow and gflow is None:
+        gflow = torch.empty_like(flow)
+    ws, ws_bytes = None, 0
+    if need_gx:
+        ws_bytes = L.usf_warp_bwd_workspace_bytes(B, C, H, W, flags)
+        if ws_bytes:
+            ws = workspace if workspace is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+            if ws.numel() * ws.element_size() < ws_bytes:
+                raise ValueError(f"workspace has {ws.numel() * ws.element_size()} bytes, need {ws_bytes}")
+    with torch.cuda.device(x.device):
+        st = L.usf_warp_bwd(x.data_ptr(), flow.data_ptr(), gout.data_ptr(),
+                            gx.data_ptr() if need_gx else None, gflow.data_ptr() if need_gflow else None,
+                            B, C, H, W, _pad(pad), _lib.F32, flags,
+                            ws.data_ptr() if ws is not None else None, ws_bytes, _stream(x))
+    _lib.check(st, "usf_warp_bwd")
+    return gx, gflow
+
+
+def launch_count():
+    return int(_lib.load().usf_launch_count())
+
+
+def reset_launch_count():
+    _lib.load().usf_reset_launch_count()
