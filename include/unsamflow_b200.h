@@ -108,7 +108,8 @@ int usf_warp_fwd(const void *x, const float *flow, void *out, int B, int C, int 
                  int pad_mode, int dtype, unsigned flags, void *stream);
 
 /* Bytes of scratch usf_warp_bwd needs when gx != NULL (0 when only gflow is wanted
- * or USF_FLAG_WARP_BWD_ATOMIC is set).  Contents need no initialisation. */
+ * or USF_FLAG_WARP_BWD_ATOMIC is set).  Contents need no initialisation; the pointer passed
+ * to usf_warp_bwd must be 16-byte aligned. */
 size_t usf_warp_bwd_workspace_bytes(int B, int C, int H, int W, unsigned flags);
 
 /*

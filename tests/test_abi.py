@@ -65,6 +65,7 @@ def test_argument_validation_without_a_gpu(lib):
     assert lib.usf_warp_bwd(p, p, p, p, p, 1, 1, 2, 2, 0, 0, 0, p, need - 1, None) == WORKSPACE
     assert lib.usf_warp_bwd_workspace_bytes(1, 1, 2, 2, 4) == 0  # atomic mode needs none
     assert lib.usf_warp_bwd_workspace_bytes(8, 32, 64, 208, 0) == 8 * 64 * 208 * (4 + 64 + 48) + 16
+    assert lib.usf_warp_bwd_workspace_bytes(1, 1, 3, 3, 0) == 48 + 16 + 9 * (64 + 48)  # cnt padded to 16 B
 
 
 def test_launch_counter_is_per_thread_and_resettable(lib):

@@ -15,7 +15,12 @@
 // keeps the 9x8 G values of the current dy in registers: per (dy, channel) it issues 4 LDS.128
 // for 72 FFMA.  Every output element is written exactly once: no atomics, no zero-fill, one
 // launch per gradient for the whole batch (the reference launches 2*B kernels).
+// When W % 4 == 0 the tiles are fetched by TMA: the X halo tile as four 8-channel boxes, the G
+// stage of gx1 as one [9][8][36] box and the SHIFTED G stage of gx2 as nine single-channel boxes
+// whose start coordinate is simply (x0+ex, y0+ey) -- the hardware zero-fill does the bounds work.
+// One producer lane feeds 4 consumer warps through full/empty mbarriers (no __syncthreads).
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace usf {
 namespace {
@@ -179,6 +184,140 @@ corr_bwd_gather(const float *__restrict__ xin, const float *__restrict__ gout, f
     }
 }
 
+
+// ===========================================================================================
+// TMA variant (W % 4 == 0): same consumer math, loads by one producer lane + mbarriers.
+// ===========================================================================================
+constexpr int NCW = CG / CT;                                 // 4 consumer warps
+constexpr int T_THREADS = 32 * (NCW + 1);                    // + 1 producer warp
+constexpr int XW_BYTES = CT * XR * XS * 4;                   // 22528: one warp's 8-channel halo box
+constexpr int G_STAGE_BYTES = G_STAGE * 4;                   // 10368
+constexpr int T_SMEM = NCW * XW_BYTES + 2 * G_STAGE_BYTES;   // 110848
+
+// mx: box [8ch][16][44] over the feature map; mg9: box [9ch][8][36] over gout (gx1);
+// mg1: box [1ch][8][36] over gout (gx2).   grid = (tiles_x, tiles_y, B * ngroups)
+template <bool GX2>
+__global__ void __launch_bounds__(T_THREADS, 2)
+corr_bwd_gather_tma(const __grid_constant__ CUtensorMap mx, const __grid_constant__ CUtensorMap mg,
+                    float *__restrict__ gx, int C, int H, int W, int ngroups, float rc) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t xfull[NCW], gfull[2], gempty[2];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int b = blockIdx.z / ngroups, cg = blockIdx.z - b * ngroups;
+    const int c0 = cg * CG;
+    if (tid == 0) {
+#pragma unroll
+        for (int w = 0; w < NCW; ++w) mbar_init(&xfull[w], 1);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&gfull[s], 1);
+            mbar_init(&gempty[s], NCW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    unsigned char *gbase = smem_raw + NCW * XW_BYTES;
+
+    if (warp == NCW) {
+        if (lane == 0) {
+            tma_prefetch_desc(&mx);
+            tma_prefetch_desc(&mg);
+            for (int dyi = 0; dyi < kD; ++dyi) {
+                const int s = dyi & 1;
+                if (dyi >= 2) mbar_wait(&gempty[s], ((dyi >> 1) - 1) & 1);
+                unsigned char *gs = gbase + s * G_STAGE_BYTES;
+                mbar_expect_tx(&gfull[s], G_STAGE_BYTES);
+                if (!GX2) {
+                    tma_load_4d(gs, &mg, &gfull[s], x0, y0, dyi * kD, b);
+                } else {
+#pragma unroll
+                    for (int dxi = 0; dxi < kD; ++dxi)
+                        tma_load_4d(gs + dxi * (TH * GS * 4), &mg, &gfull[s], x0 + dxi - kMaxDisp,
+                                    y0 + dyi - kMaxDisp, kK - 1 - (dyi * kD + dxi), b);
+                }
+                if (dyi == 0) {  // the X halo tiles go out right after the first G stage
+#pragma unroll
+                    for (int w = 0; w < NCW; ++w) {
+                        mbar_expect_tx(&xfull[w], XW_BYTES);
+                        tma_load_4d(smem_raw + w * XW_BYTES, &mx, &xfull[w], x0 - kMaxDisp, y0 - kMaxDisp,
+                                    c0 + w * CT, b);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    const int r = lane >> 2, q = lane & 3;
+    float acc[CT][8];
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
+
+    const float *xw = reinterpret_cast<const float *>(smem_raw + warp * XW_BYTES) + r * XS + 8 * q;
+    mbar_wait(&xfull[warp], 0);
+#pragma unroll 1
+    for (int dyi = 0; dyi < kD; ++dyi) {
+        const int s = dyi & 1;
+        mbar_wait(&gfull[s], (dyi >> 1) & 1);
+        const float *gs = reinterpret_cast<const float *>(gbase + s * G_STAGE_BYTES) + r * GS + 8 * q;
+        float g[kD][8];
+#pragma unroll
+        for (int dx = 0; dx < kD; ++dx) {
+            const float4 g0 = lds128(gs + dx * TH * GS), g1 = lds128(gs + dx * TH * GS + 4);
+            g[dx][0] = g0.x; g[dx][1] = g0.y; g[dx][2] = g0.z; g[dx][3] = g0.w;
+            g[dx][4] = g1.x; g[dx][5] = g1.y; g[dx][6] = g1.z; g[dx][7] = g1.w;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&gempty[s]);  // G values now live in registers
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const float *p = xw + (c * XR + dyi) * XS;
+            const float4 w0 = lds128(p), w1 = lds128(p + 4), w2 = lds128(p + 8), w3 = lds128(p + 12);
+            const float w[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
+                                 w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+            for (int dx = 0; dx < kD; ++dx)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(g[dx][i], w[dx + i], acc[c][i]);
+        }
+    }
+
+    const int gy = y0 + r, gxx = x0 + 8 * q;
+    if (gy >= H) return;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+        const int cc = c0 + warp * CT + c;
+        if (cc >= C) break;
+        float *o = gx + (((size_t)b * C + cc) * H + gy) * W + gxx;
+        if (gxx < W)
+            *reinterpret_cast<float4 *>(o) =
+                make_float4(acc[c][0] * rc, acc[c][1] * rc, acc[c][2] * rc, acc[c][3] * rc);
+        if (gxx + 4 < W)
+            *reinterpret_cast<float4 *>(o + 4) =
+                make_float4(acc[c][4] * rc, acc[c][5] * rc, acc[c][6] * rc, acc[c][7] * rc);
+    }
+}
+
+template <bool GX2>
+cudaError_t launch_tma(const CUtensorMap &mx, const CUtensorMap &mg, float *gx, int B, int C, int H, int W,
+                       cudaStream_t stream) {
+    static cudaError_t once = [] {
+        cudaError_t e = cudaFuncSetAttribute(corr_bwd_gather_tma<GX2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             T_SMEM);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(corr_bwd_gather_tma<GX2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared);
+    }();
+    if (once != cudaSuccess) return once;
+    const int ngroups = (C + CG - 1) / CG;
+    dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B * ngroups);
+    corr_bwd_gather_tma<GX2><<<grid, T_THREADS, T_SMEM, stream>>>(mx, mg, gx, C, H, W, ngroups, 1.0f / (float)C);
+    return cudaGetLastError();
+}
+
 template <bool GX2, bool VEC>
 cudaError_t launch(const float *xin, const float *gout, float *gx, int B, int C, int H, int W,
                    cudaStream_t stream) {
@@ -199,6 +338,24 @@ int corr_bwd_f32(const float *x1, const float *x2, const float *gout, float *gx1
     const bool vec = (W % 4 == 0) &&
                      (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)gout | (uintptr_t)gx1 | (uintptr_t)gx2) % 16 == 0);
     int st = USF_OK;
+    if (vec) {
+        // TMA path (tensor maps encoded per call, passed as __grid_constant__ parameters)
+        CUtensorMap mx, mg;
+        bool ok = true;
+        if (gx1) {
+            ok = make_nchw_map(&mx, x2, B, C, H, W, XS, XR, CT) && make_nchw_map(&mg, gout, B, kK, H, W, GS, TH, kD);
+            if (ok) {
+                st = note_launch(launch_tma<false>(mx, mg, gx1, B, C, H, W, stream));
+                if (st != USF_OK) return st;
+            }
+        }
+        if (ok && gx2) {
+            ok = make_nchw_map(&mx, x1, B, C, H, W, XS, XR, CT) && make_nchw_map(&mg, gout, B, kK, H, W, GS, TH, 1);
+            if (ok) return note_launch(launch_tma<true>(mx, mg, gx2, B, C, H, W, stream));
+        }
+        if (ok) return st;
+        // encoding failed (driver entry point missing): fall through to the cp.async kernels
+    }
     if (gx1) {
         cudaError_t e = vec ? launch<false, true>(x2, gout, gx1, B, C, H, W, stream)
                             : launch<false, false>(x2, gout, gx1, B, C, H, W, stream);

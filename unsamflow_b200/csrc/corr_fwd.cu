@@ -12,11 +12,16 @@
 //   * a thread owns 8 consecutive pixels of one row and the 9 dx of ONE dy: 72 fp32
 //     accumulators; per channel it issues 2 + 4 LDS.128 (x1 strip, 16-wide x2 window) for
 //     72 FFMA.  Row strides of 9 and 11 16-byte chunks make every LDS.128 phase conflict-free;
+//   * when W % 4 == 0 the stages are filled by TMA (cp.async.bulk.tensor 4-D boxes, hardware
+//     zero-fill for halo / ragged tails) issued by one producer thread and handed to the consumer
+//     warps through full/empty mbarriers: no address arithmetic and no __syncthreads in the loop;
+//     the cp.async kernels below remain as the path for odd widths (W = 13, 26, ...);
 //   * kernel A ("tile9"): 9 warps = 9 dy, every warp walks all channels (big levels);
 //   * kernel B ("splitc"): CTA = (tile, dy), 8 warps take every 8th channel and their partial
 //     tiles are summed through shared memory in a fixed order (small levels: few pixels, many
 //     channels -> 9x more CTAs, no y-halo).  Deterministic either way.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace usf {
 namespace {
@@ -241,6 +246,201 @@ corr_fwd_splitc(const float *__restrict__ x1, const float *__restrict__ x2, floa
     }
 }
 
+
+// ===========================================================================================
+// TMA variants (W % 4 == 0).  Same thread <-> data mapping and the same fma_channel as above.
+// ===========================================================================================
+template <bool LEAKY>
+__device__ __forceinline__ float finish_t(float v, float rc, float slope) {
+    v *= rc;
+    if (LEAKY) v = v < 0.f ? v * slope : v;
+    return v;
+}
+
+constexpr int TA_THREADS = 32 * (kD + 1);                  // 9 consumer warps + 1 producer warp
+constexpr int X1_BYTES = CK * TH * X1S * 4;                // 9216  (box 36 x 8 x 8)
+constexpr int TA_X2_BYTES = CK * A_ROWS2 * X2S * 4;        // 22528 (box 44 x 16 x 8)
+constexpr int TA_STAGE_BYTES = X1_BYTES + TA_X2_BYTES;     // 31744
+constexpr int TA_SMEM = NST * TA_STAGE_BYTES;              // 95232
+
+// grid = (tiles_x, tiles_y, B)
+template <bool LEAKY>
+__global__ void __launch_bounds__(TA_THREADS, 2)
+corr_fwd_tile9_tma(const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
+                   float *__restrict__ out, int C, int H, int W, float rc, float slope) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[NST], empty_bar[NST];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
+    const int nchunk = (C + CK - 1) / CK;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NST; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kD);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kD) {  // producer warp: one lane feeds the ring
+        if (lane == 0) {
+            tma_prefetch_desc(&m1);
+            tma_prefetch_desc(&m2);
+            for (int k = 0; k < nchunk; ++k) {
+                const int s = k % NST;
+                if (k >= NST) mbar_wait(&empty_bar[s], ((k / NST) - 1) & 1);
+                unsigned char *st = smem_raw + s * TA_STAGE_BYTES;
+                mbar_expect_tx(&full_bar[s], TA_STAGE_BYTES);
+                tma_load_4d(st, &m1, &full_bar[s], x0, y0, k * CK, b);
+                tma_load_4d(st + X1_BYTES, &m2, &full_bar[s], x0 - kMaxDisp, y0 - kMaxDisp, k * CK, b);
+            }
+        }
+        return;
+    }
+
+    const int r = lane >> 2, q = lane & 3;
+    float acc[kD][8];
+#pragma unroll
+    for (int dx = 0; dx < kD; ++dx)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[dx][i] = 0.f;
+
+    for (int k = 0; k < nchunk; ++k) {
+        const int s = k % NST;
+        mbar_wait(&full_bar[s], (k / NST) & 1);
+        const float *st = reinterpret_cast<const float *>(smem_raw + s * TA_STAGE_BYTES);
+        const float *p1 = st + r * X1S + 8 * q;
+        const float *p2 = st + CK * TH * X1S + (r + warp) * X2S + 8 * q;
+#pragma unroll 2
+        for (int c = 0; c < CK; ++c) fma_channel(acc, p1 + c * TH * X1S, p2 + c * A_ROWS2 * X2S);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+
+    const int gy = y0 + r, gx = x0 + 8 * q;
+    if (gy >= H) return;
+    float *o = out + (((size_t)b * kK + warp * kD) * H + gy) * W + gx;
+    const size_t kstride = (size_t)H * W;
+#pragma unroll
+    for (int dx = 0; dx < kD; ++dx, o += kstride) {
+        if (gx < W)
+            *reinterpret_cast<float4 *>(o) =
+                make_float4(finish_t<LEAKY>(acc[dx][0], rc, slope), finish_t<LEAKY>(acc[dx][1], rc, slope),
+                            finish_t<LEAKY>(acc[dx][2], rc, slope), finish_t<LEAKY>(acc[dx][3], rc, slope));
+        if (gx + 4 < W)
+            *reinterpret_cast<float4 *>(o + 4) =
+                make_float4(finish_t<LEAKY>(acc[dx][4], rc, slope), finish_t<LEAKY>(acc[dx][5], rc, slope),
+                            finish_t<LEAKY>(acc[dx][6], rc, slope), finish_t<LEAKY>(acc[dx][7], rc, slope));
+    }
+}
+
+constexpr int TB_THREADS = 32 * (B_WARPS + 1);             // 8 consumer warps + 1 producer warp
+constexpr int TB_NST = 4;
+constexpr int TB_X2_BYTES = CK * TH * X2S * 4;             // 11264 (box 44 x 8 x 8)
+constexpr int TB_STAGE_BYTES = X1_BYTES + TB_X2_BYTES;     // 20480
+constexpr int TB_SMEM = (B_RED * 4 > TB_NST * TB_STAGE_BYTES) ? B_RED * 4 : TB_NST * TB_STAGE_BYTES;
+
+// grid = (tiles_x, tiles_y, B * 9)
+template <bool LEAKY>
+__global__ void __launch_bounds__(TB_THREADS, 2)
+corr_fwd_splitc_tma(const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
+                    float *__restrict__ out, int C, int H, int W, float rc, float slope) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[TB_NST], empty_bar[TB_NST];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int b = blockIdx.z / kD, dyi = blockIdx.z - b * kD;
+    const int nchunk = (C + CK - 1) / CK;
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < TB_NST; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], B_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == B_WARPS) {
+        if (lane == 0) {
+            tma_prefetch_desc(&m1);
+            tma_prefetch_desc(&m2);
+            for (int k = 0; k < nchunk; ++k) {
+                const int s = k % TB_NST;
+                if (k >= TB_NST) mbar_wait(&empty_bar[s], ((k / TB_NST) - 1) & 1);
+                unsigned char *st = smem_raw + s * TB_STAGE_BYTES;
+                mbar_expect_tx(&full_bar[s], TB_STAGE_BYTES);
+                tma_load_4d(st, &m1, &full_bar[s], x0, y0, k * CK, b);
+                tma_load_4d(st + X1_BYTES, &m2, &full_bar[s], x0 - kMaxDisp, y0 + dyi - kMaxDisp, k * CK, b);
+            }
+        }
+        return;
+    }
+
+    const int r = lane >> 2, q = lane & 3;
+    float acc[kD][8];
+#pragma unroll
+    for (int dx = 0; dx < kD; ++dx)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[dx][i] = 0.f;
+
+    for (int k = 0; k < nchunk; ++k) {
+        const int s = k % TB_NST;
+        mbar_wait(&full_bar[s], (k / TB_NST) & 1);
+        const float *st = reinterpret_cast<const float *>(smem_raw + s * TB_STAGE_BYTES);
+        fma_channel(acc, st + (warp * TH + r) * X1S + 8 * q, st + CK * TH * X1S + (warp * TH + r) * X2S + 8 * q);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+    // all 8 consumer warps are past their last stage read -> reuse the ring for the reduction
+    asm volatile("bar.sync 1, %0;\n" ::"n"(32 * B_WARPS) : "memory");
+    float *smem = reinterpret_cast<float *>(smem_raw);
+    float *red = smem + (size_t)warp * (kD * TH * X1S);
+#pragma unroll
+    for (int dx = 0; dx < kD; ++dx) {
+        float *p = red + (dx * TH + r) * X1S + 8 * q;
+        *reinterpret_cast<float4 *>(p) = make_float4(acc[dx][0], acc[dx][1], acc[dx][2], acc[dx][3]);
+        *reinterpret_cast<float4 *>(p + 4) = make_float4(acc[dx][4], acc[dx][5], acc[dx][6], acc[dx][7]);
+    }
+    asm volatile("bar.sync 1, %0;\n" ::"n"(32 * B_WARPS) : "memory");
+    float *ob = out + ((size_t)b * kK + dyi * kD) * H * W;
+#pragma unroll
+    for (int m = 0; m < kD; ++m) {
+        const int e = tid + m * (32 * B_WARPS);
+        const int dx = e >> 8, rr = (e >> 5) & 7, col = e & 31;
+        const float *p = smem + (dx * TH + rr) * X1S + col;
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < B_WARPS; ++w) sum += p[w * (kD * TH * X1S)];
+        const int gy = y0 + rr, gx = x0 + col;
+        if (gy < H && gx < W) ob[((size_t)dx * H + gy) * W + gx] = finish_t<LEAKY>(sum, rc, slope);
+    }
+}
+
+template <typename K>
+cudaError_t prep(K kernel, int smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+template <bool LEAKY>
+cudaError_t launch_tma(bool splitc, const CUtensorMap &m1, const CUtensorMap &m2a, const CUtensorMap &m2b,
+                       float *out, int B, int C, int H, int W, int tx, int ty, float rc, float slope,
+                       cudaStream_t stream) {
+    if (splitc) {
+        static cudaError_t once = prep(corr_fwd_splitc_tma<LEAKY>, TB_SMEM);
+        if (once != cudaSuccess) return once;
+        corr_fwd_splitc_tma<LEAKY><<<dim3(tx, ty, B * kD), TB_THREADS, TB_SMEM, stream>>>(m1, m2b, out, C, H, W, rc, slope);
+    } else {
+        static cudaError_t once = prep(corr_fwd_tile9_tma<LEAKY>, TA_SMEM);
+        if (once != cudaSuccess) return once;
+        corr_fwd_tile9_tma<LEAKY><<<dim3(tx, ty, B), TA_THREADS, TA_SMEM, stream>>>(m1, m2a, out, C, H, W, rc, slope);
+    }
+    return cudaGetLastError();
+}
+
 template <typename K>
 cudaError_t set_smem(K kernel, int bytes) {
     return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -257,6 +457,17 @@ int corr_fwd_f32(const float *x1, const float *x2, float *out, int B, int C, int
     // Few tiles and many channels: split dy over CTAs and channels over warps.
     const long tiles = (long)tx * ty * B;
     const bool splitc = tiles < 2 * 148 && C >= 48;
+    if (vec) {
+        // TMA path: tensor maps are encoded on the host per call (pointers differ per call) and travel
+        // as __grid_constant__ kernel parameters; nothing is cached between calls (re-entrant).
+        CUtensorMap m1, m2;
+        if (make_nchw_map(&m1, x1, B, C, H, W, X1S, TH, CK) &&
+            make_nchw_map(&m2, x2, B, C, H, W, X2S, splitc ? TH : A_ROWS2, CK)) {
+            cudaError_t et = leaky ? launch_tma<true>(splitc, m1, m2, m2, out, B, C, H, W, tx, ty, rc, slope, stream)
+                                   : launch_tma<false>(splitc, m1, m2, m2, out, B, C, H, W, tx, ty, rc, slope, stream);
+            return note_launch(et);
+        }
+    }
     cudaError_t e;
     if (splitc) {
         dim3 grid(tx, ty, B * kD);

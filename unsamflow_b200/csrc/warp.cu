@@ -123,13 +123,15 @@ struct Workspace {
     int *ovf_src;
     float *ovf_w;
 };
+// cnt is padded to a multiple of 16 bytes so that ent (read as int4) stays 16-byte aligned
+__host__ __device__ inline size_t cnt_bytes(size_t N) { return (N * 4 + 15) / 16 * 16; }
 __host__ __device__ inline size_t ws_bytes(size_t N) {
-    return N * 4 + 16 + N * kSlots * 8 + 3 * (4 * N) * 4;
+    return cnt_bytes(N) + 16 + N * kSlots * 8 + 3 * (4 * N) * 4;
 }
 inline Workspace carve(void *base, size_t N) {
     char *p = (char *)base;
     Workspace w;
-    w.cnt = (int *)p;               p += N * 4;
+    w.cnt = (int *)p;               p += cnt_bytes(N);
     w.ovf_n = (int *)p;             p += 16;
     w.ent = (int2 *)p;              p += N * kSlots * 8;
     w.ovf_tgt = (int *)p;           p += 4 * N * 4;
@@ -351,9 +353,10 @@ int warp_bwd_f32(const float *x, const float *flow, const float *gout, float *gx
         if (e != cudaSuccess) { note_cuda_error(e); return USF_ERR_CUDA; }
         return note_launch(launch_bwd<2>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
     }
-    if (workspace == nullptr || workspace_bytes < ws_bytes((size_t)N)) return USF_ERR_WORKSPACE;
+    if (workspace == nullptr || workspace_bytes < ws_bytes((size_t)N) || ((uintptr_t)workspace & 15))
+        return USF_ERR_WORKSPACE;
     ws = carve(workspace, (size_t)N);
-    cudaError_t e = cudaMemsetAsync(ws.cnt, 0, (size_t)N * 4 + 16, stream);
+    cudaError_t e = cudaMemsetAsync(ws.cnt, 0, cnt_bytes((size_t)N) + 16, stream);
     if (e != cudaSuccess) { note_cuda_error(e); return USF_ERR_CUDA; }
     int st = note_launch(launch_bwd<1>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
     if (st != USF_OK) return st;
