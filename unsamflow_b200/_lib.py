@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libunsamflow_b200.so")
+# USF_LIB_PATH overrides the library location (A/B runs against another build of the same ABI)
+LIB_PATH = os.environ.get("USF_LIB_PATH") or os.path.join(_PKG, "lib", "libunsamflow_b200.so")
 
 ABI_VERSION = 1
 F32, BF16 = 0, 1

@@ -15,10 +15,10 @@
 // keeps the 9x8 G values of the current dy in registers: per (dy, channel) it issues 4 LDS.128
 // for 72 FFMA.  Every output element is written exactly once: no atomics, no zero-fill, one
 // launch per gradient for the whole batch (the reference launches 2*B kernels).
-// When W % 4 == 0 the tiles are fetched by TMA: the X halo tile as four 8-channel boxes, the G
-// stage of gx1 as one [9][8][36] box and the SHIFTED G stage of gx2 as nine single-channel boxes
-// whose start coordinate is simply (x0+ex, y0+ey) -- the hardware zero-fill does the bounds work.
-// One producer lane feeds 4 consumer warps through full/empty mbarriers (no __syncthreads).
+// When W % 4 == 0 the tiles are fetched by TMA (hardware zero-fill does the bounds work): the X halo
+// tile as four 8-channel boxes, the G stage as one 9-channel box (see the TMA section below for how
+// the shifted G tile of gx2 is handled).  One producer lane feeds 4 consumer warps through
+// full/empty mbarriers (no __syncthreads in the loop).
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -187,21 +187,72 @@ corr_bwd_gather(const float *__restrict__ xin, const float *__restrict__ gout, f
 
 // ===========================================================================================
 // TMA variant (W % 4 == 0): same consumer math, loads by one producer lane + mbarriers.
+//
+// TMA constraint found the hard way (sm_100a, driver 580): the innermost box coordinate must be a
+// multiple of 16 bytes -- a box starting at x0+ex with ex % 4 != 0 raises "illegal instruction".
+// So the SHIFTED G tile of gx2 is fetched as ONE aligned halo box [9 ch][8 rows][44 cols] at
+// (x0-4, y0+ey, channel (8-dyi)*9): slot j holds gO channel (8-dyi)*9+j, displacement dxi needs
+// channel 80-k = slot 8-dxi, and its 8 values start at column 8q+dxi of that row.  dxi is a
+// compile-time constant in the unrolled consumer loop, so the unaligned window is read as 2-3
+// aligned LDS.128 and selected with static register indices.
 // ===========================================================================================
 constexpr int NCW = CG / CT;                                 // 4 consumer warps
 constexpr int T_THREADS = 32 * (NCW + 1);                    // + 1 producer warp
 constexpr int XW_BYTES = CT * XR * XS * 4;                   // 22528: one warp's 8-channel halo box
-constexpr int G_STAGE_BYTES = G_STAGE * 4;                   // 10368
-constexpr int T_SMEM = NCW * XW_BYTES + 2 * G_STAGE_BYTES;   // 110848
+constexpr int NBAR = NCW + 4;                                // xfull[4], gfull[2], gempty[2]
 
-// mx: box [8ch][16][44] over the feature map; mg9: box [9ch][8][36] over gout (gx1);
-// mg1: box [1ch][8][36] over gout (gx2).   grid = (tiles_x, tiles_y, B * ngroups)
+template <bool GX2> struct GTile {
+    static constexpr int kStride = GX2 ? XS : GS;            // 44 (halo box) : 36
+    static constexpr int kBytes = kD * TH * kStride * 4;     // 12672 : 10368
+    static constexpr int kSmem = NCW * XW_BYTES + 2 * kBytes + NBAR * 8;  // barriers live at the end
+};
+
+// eight G values of displacement dxi for this thread's pixels (row base pointer `row`)
+template <bool GX2, int DXI>
+__device__ __forceinline__ void load_g(float (&g)[8], const float *__restrict__ stage, int r, int q) {
+    constexpr int S = GTile<GX2>::kStride;
+    if (!GX2) {
+        const float *p = stage + (DXI * TH + r) * S + 8 * q;
+        const float4 a = lds128(p), b = lds128(p + 4);
+        g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+    } else {
+        constexpr int A = 4 * (DXI / 4), O = DXI - A;
+        const float *p = stage + ((kD - 1 - DXI) * TH + r) * S + 8 * q + A;
+        const float4 a = lds128(p), b = lds128(p + 4);
+        if (O == 0) {
+            g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+        } else {
+            const float4 c = lds128(p + 8);
+            const float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = v[O + i];
+        }
+    }
+}
+
+template <bool GX2, int DXI>
+struct GLoader {
+    static __device__ __forceinline__ void run(float (&g)[kD][8], const float *stage, int r, int q) {
+        load_g<GX2, DXI>(g[DXI], stage, r, q);
+        GLoader<GX2, DXI + 1>::run(g, stage, r, q);
+    }
+};
+template <bool GX2>
+struct GLoader<GX2, kD> {
+    static __device__ __forceinline__ void run(float (&)[kD][8], const float *, int, int) {}
+};
+
+// mx: box [8ch][16][44] over the feature map.  mg over gout: gx1 box [9ch][8][36], gx2 box [9ch][8][44].
+// grid = (tiles_x, tiles_y, B * ngroups)
 template <bool GX2>
 __global__ void __launch_bounds__(T_THREADS, 2)
 corr_bwd_gather_tma(const __grid_constant__ CUtensorMap mx, const __grid_constant__ CUtensorMap mg,
                     float *__restrict__ gx, int C, int H, int W, int ngroups, float rc) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t xfull[NCW], gfull[2], gempty[2];
+    constexpr int GB = GTile<GX2>::kBytes;
+    unsigned char *gbase = smem_raw + NCW * XW_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(gbase + 2 * GB);
+    uint64_t *xfull = bars, *gfull = bars + NCW, *gempty = bars + NCW + 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const int b = blockIdx.z / ngroups, cg = blockIdx.z - b * ngroups;
@@ -217,27 +268,23 @@ corr_bwd_gather_tma(const __grid_constant__ CUtensorMap mx, const __grid_constan
         mbar_fence_init();
     }
     __syncthreads();
-    unsigned char *gbase = smem_raw + NCW * XW_BYTES;
 
     if (warp == NCW) {
         if (lane == 0) {
             tma_prefetch_desc(&mx);
             tma_prefetch_desc(&mg);
+#pragma unroll 1
             for (int dyi = 0; dyi < kD; ++dyi) {
                 const int s = dyi & 1;
                 if (dyi >= 2) mbar_wait(&gempty[s], ((dyi >> 1) - 1) & 1);
-                unsigned char *gs = gbase + s * G_STAGE_BYTES;
-                mbar_expect_tx(&gfull[s], G_STAGE_BYTES);
-                if (!GX2) {
-                    tma_load_4d(gs, &mg, &gfull[s], x0, y0, dyi * kD, b);
-                } else {
-#pragma unroll
-                    for (int dxi = 0; dxi < kD; ++dxi)
-                        tma_load_4d(gs + dxi * (TH * GS * 4), &mg, &gfull[s], x0 + dxi - kMaxDisp,
-                                    y0 + dyi - kMaxDisp, kK - 1 - (dyi * kD + dxi), b);
-                }
+                mbar_expect_tx(&gfull[s], GB);
+                if (!GX2)
+                    tma_load_4d(gbase + s * GB, &mg, &gfull[s], x0, y0, dyi * kD, b);
+                else
+                    tma_load_4d(gbase + s * GB, &mg, &gfull[s], x0 - kMaxDisp, y0 + dyi - kMaxDisp,
+                                (kD - 1 - dyi) * kD, b);
                 if (dyi == 0) {  // the X halo tiles go out right after the first G stage
-#pragma unroll
+#pragma unroll 1
                     for (int w = 0; w < NCW; ++w) {
                         mbar_expect_tx(&xfull[w], XW_BYTES);
                         tma_load_4d(smem_raw + w * XW_BYTES, &mx, &xfull[w], x0 - kMaxDisp, y0 - kMaxDisp,
@@ -262,14 +309,8 @@ corr_bwd_gather_tma(const __grid_constant__ CUtensorMap mx, const __grid_constan
     for (int dyi = 0; dyi < kD; ++dyi) {
         const int s = dyi & 1;
         mbar_wait(&gfull[s], (dyi >> 1) & 1);
-        const float *gs = reinterpret_cast<const float *>(gbase + s * G_STAGE_BYTES) + r * GS + 8 * q;
         float g[kD][8];
-#pragma unroll
-        for (int dx = 0; dx < kD; ++dx) {
-            const float4 g0 = lds128(gs + dx * TH * GS), g1 = lds128(gs + dx * TH * GS + 4);
-            g[dx][0] = g0.x; g[dx][1] = g0.y; g[dx][2] = g0.z; g[dx][3] = g0.w;
-            g[dx][4] = g1.x; g[dx][5] = g1.y; g[dx][6] = g1.z; g[dx][7] = g1.w;
-        }
+        GLoader<GX2, 0>::run(g, reinterpret_cast<const float *>(gbase + s * GB), r, q);
         __syncwarp();
         if (lane == 0) mbar_arrive(&gempty[s]);  // G values now live in registers
 #pragma unroll
@@ -304,9 +345,9 @@ corr_bwd_gather_tma(const __grid_constant__ CUtensorMap mx, const __grid_constan
 template <bool GX2>
 cudaError_t launch_tma(const CUtensorMap &mx, const CUtensorMap &mg, float *gx, int B, int C, int H, int W,
                        cudaStream_t stream) {
+    constexpr int SM = GTile<GX2>::kSmem;
     static cudaError_t once = [] {
-        cudaError_t e = cudaFuncSetAttribute(corr_bwd_gather_tma<GX2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             T_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(corr_bwd_gather_tma<GX2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(corr_bwd_gather_tma<GX2>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared);
@@ -314,7 +355,7 @@ cudaError_t launch_tma(const CUtensorMap &mx, const CUtensorMap &mg, float *gx, 
     if (once != cudaSuccess) return once;
     const int ngroups = (C + CG - 1) / CG;
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B * ngroups);
-    corr_bwd_gather_tma<GX2><<<grid, T_THREADS, T_SMEM, stream>>>(mx, mg, gx, C, H, W, ngroups, 1.0f / (float)C);
+    corr_bwd_gather_tma<GX2><<<grid, T_THREADS, SM, stream>>>(mx, mg, gx, C, H, W, ngroups, 1.0f / (float)C);
     return cudaGetLastError();
 }
 
@@ -350,7 +391,7 @@ int corr_bwd_f32(const float *x1, const float *x2, const float *gout, float *gx1
             }
         }
         if (ok && gx2) {
-            ok = make_nchw_map(&mx, x1, B, C, H, W, XS, XR, CT) && make_nchw_map(&mg, gout, B, kK, H, W, GS, TH, 1);
+            ok = make_nchw_map(&mx, x1, B, C, H, W, XS, XR, CT) && make_nchw_map(&mg, gout, B, kK, H, W, XS, TH, kD);
             if (ok) return note_launch(launch_tma<true>(mx, mg, gx2, B, C, H, W, stream));
         }
         if (ok) return st;

@@ -10,6 +10,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace usf {
 
@@ -33,8 +34,18 @@ inline EncodeTiledFn encode_tiled_fn() {
 }
 
 // NCHW fp32 tensor [B,C,H,W] -> map with box [1][bc][bh][bw].  Returns false if TMA cannot be used.
+// USF_DISABLE_TMA=1 in the environment forces the cp.async kernels (A/B measurements, debugging).
+inline bool tma_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("USF_DISABLE_TMA");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
+
 inline bool make_nchw_map(CUtensorMap *map, const float *base, int B, int C, int H, int W, int bw, int bh,
                           int bc) {
+    if (!tma_enabled()) return false;
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn || (W % 4) != 0 || ((uintptr_t)base & 15) != 0) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
