@@ -1,0 +1,98 @@
+#!/usr/bin/env python
+"""Per-op microbenchmark (BASELINE.json configs[4]): CUDA-event timing of single ops through the C ABI.
+
+  python benchmarks/microbench.py --ops corr_fwd,corr_bwd --shapes 8x32x64x208,8x64x32x104 [--cold]
+
+Each (op, shape) is captured in a CUDA graph holding `--inner` back-to-back launches so that Python
+launch overhead does not pollute the number; --cold flushes L2 before every graph replay (then
+inner is forced to 1).  Prints one JSON line per (op, shape) and an optional table file.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from unsamflow_b200 import hotpath, ops  # noqa: E402
+
+KITTI = ["8x192x4x13", "8x128x8x26", "8x96x16x52", "8x64x32x104", "8x32x64x208"]
+
+
+def build(op, shape, sigma):
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(1)
+    dev = "cuda"
+    x1 = torch.randn(B, C, H, W, generator=g).to(dev)
+    x2 = torch.randn(B, C, H, W, generator=g).to(dev)
+    if op == "corr_fwd":
+        out = torch.empty(B, 81, H, W, device=dev)
+        return (lambda: ops.corr_fwd(x1, x2, out=out)), hotpath.corr_fwd_bytes(*shape), hotpath.corr_fwd_flops(*shape), 1
+    if op == "corr_bwd":
+        go = torch.randn(B, 81, H, W, generator=g).to(dev)
+        g1, g2 = torch.empty_like(x1), torch.empty_like(x2)
+        return (lambda: ops.corr_bwd(x1, x2, go, gx1=g1, gx2=g2)), hotpath.corr_bwd_bytes(*shape), 2 * hotpath.corr_fwd_flops(*shape), 2
+    fl = (sigma * torch.randn(B, 2, H, W, generator=g)).to(dev)
+    if op == "warp_fwd":
+        out = torch.empty_like(x1)
+        return (lambda: ops.warp_fwd(x1, fl, "border", out=out)), hotpath.warp_fwd_bytes(*shape), 0, 1
+    if op in ("warp_bwd", "warp_bwd_atomic"):
+        atomic = op.endswith("atomic")
+        gx, gf = torch.empty_like(x1), torch.empty_like(fl)
+        ws = None if atomic else torch.empty(ops.warp_bwd_workspace_bytes(x1), dtype=torch.uint8, device=dev)
+        return (lambda: ops.warp_bwd(x1, fl, x2, "border", gx=gx, gflow=gf, workspace=ws, atomic=atomic)), \
+            hotpath.warp_bwd_bytes(*shape), 0, (1 if atomic else 3)
+    if op == "warp_bwd_flow":
+        gf = torch.empty_like(fl)
+        return (lambda: ops.warp_bwd(x1, fl, x2, "border", need_gx=False, gflow=gf)), \
+            hotpath.warp_bwd_bytes(*shape, need_gx=False), 0, 1
+    raise ValueError(op)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ops", default="corr_fwd,corr_bwd,warp_fwd,warp_bwd,warp_bwd_flow")
+    ap.add_argument("--shapes", default=",".join(KITTI))
+    ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--inner", type=int, default=10)
+    ap.add_argument("--cold", action="store_true")
+    ap.add_argument("--sigma", type=float, default=3.0)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    inner = 1 if args.cold else args.inner
+    rows = []
+    for op in args.ops.split(","):
+        for s in args.shapes.split(","):
+            shape = tuple(int(v) for v in s.split("x"))
+            fn, nbytes, flops, launches = build(op, shape, args.sigma)
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for _ in range(inner):
+                    fn()
+            ts = []
+            for _ in range(args.iters):
+                if args.cold:
+                    flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); graph.replay(); b.record()
+                b.synchronize()
+                ts.append(a.elapsed_time(b) * 1e3 / inner)
+            us = statistics.median(ts)
+            row = {"op": op, "shape": s, "us": round(us, 2), "min_us": round(min(ts), 2), "launches": launches,
+                   "GBps": round(nbytes / us / 1e3, 1), "TFLOPs": round(flops / us / 1e6, 2),
+                   "l2": "cold" if args.cold else "warm"}
+            rows.append(row)
+            print(json.dumps(row), flush=True)
+    if args.out:
+        with open(args.out, "w") as f:
+            json.dump(rows, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

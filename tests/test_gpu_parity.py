@@ -390,3 +390,17 @@ def test_cuda_graph_capture_of_a_step(usf):
     torch.cuda.synchronize()
     for k, v in eager.items():
         assert torch.allclose(step.t[k], v, rtol=1e-5, atol=1e-6), k
+
+
+def test_fallback_kernels_in_a_subprocess(usf):
+    """USF_DISABLE_TMA=1 + USF_DIRECT_MAX_PIXELS=0 force the cp.async kernels that normally only serve
+    large odd-width shapes; they must pass the same golden / oracle checks."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, USF_DISABLE_TMA="1", USF_DIRECT_MAX_PIXELS="0")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(here, "test_gpu_parity.py"),
+                        "-k", "golden or corr_vs_oracle or nullable"], env=env, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]

@@ -1,5 +1,7 @@
 // api.cu -- the extern "C" boundary declared in include/unsamflow_b200.h.
 // Validates arguments, dispatches on dtype, never allocates, never synchronises.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace usf {
@@ -11,6 +13,11 @@ int warp_fwd_f32(const float *, const float *, float *, int, int, int, int, int,
 int warp_bwd_f32(const float *, const float *, const float *, float *, float *, int, int, int, int, int,
                  unsigned, void *, size_t, cudaStream_t);
 size_t warp_bwd_workspace_bytes(size_t N);
+
+long kDirectMaxPixels = [] {
+    const char *e = getenv("USF_DIRECT_MAX_PIXELS");
+    return e ? atol(e) : 4096L;
+}();
 
 static thread_local int tl_cuda_error = 0;
 static thread_local unsigned long long tl_launches = 0;

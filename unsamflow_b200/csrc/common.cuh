@@ -10,6 +10,9 @@ namespace usf {
 constexpr int kMaxDisp = 4;            // PWC-Lite search range (models/pwclite.py:182)
 constexpr int kD = 2 * kMaxDisp + 1;   // 9
 constexpr int kK = kD * kD;            // 81 displacement channels
+// B*H*W at or below which the direct (no shared memory) corr kernels are used; override with
+// USF_DIRECT_MAX_PIXELS for A/B runs
+extern long kDirectMaxPixels;
 
 // ---- host-side bookkeeping (api.cu) ---------------------------------------
 int note_launch(cudaError_t e);        // counts a launch, records e; returns usf_status

@@ -374,8 +374,12 @@ cudaError_t launch(const float *xin, const float *gout, float *gx, int B, int C,
 
 }  // namespace
 
+int corr_bwd_direct_f32(const float *, const float *, const float *, float *, float *, int, int, int, int,
+                        cudaStream_t);
+
 int corr_bwd_f32(const float *x1, const float *x2, const float *gout, float *gx1, float *gx2, int B, int C,
                  int H, int W, cudaStream_t stream) {
+    if ((long)B * H * W <= kDirectMaxPixels) return corr_bwd_direct_f32(x1, x2, gout, gx1, gx2, B, C, H, W, stream);
     const bool vec = (W % 4 == 0) &&
                      (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)gout | (uintptr_t)gx1 | (uintptr_t)gx2) % 16 == 0);
     int st = USF_OK;

@@ -448,8 +448,12 @@ cudaError_t set_smem(K kernel, int bytes) {
 
 }  // namespace
 
+int corr_fwd_direct_f32(const float *, const float *, float *, int, int, int, int, unsigned, float, cudaStream_t);
+
 int corr_fwd_f32(const float *x1, const float *x2, float *out, int B, int C, int H, int W, unsigned flags,
                  float slope, cudaStream_t stream) {
+    // tiny levels (KITTI 4x13, 8x26): latency-bound, L1/L2 resident -> direct kernel (corr_direct.cu)
+    if ((long)B * H * W <= kDirectMaxPixels) return corr_fwd_direct_f32(x1, x2, out, B, C, H, W, flags, slope, stream);
     const bool vec = (W % 4 == 0) && (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) % 16 == 0);
     const int tx = (W + TW - 1) / TW, ty = (H + TH - 1) / TH;
     const float rc = 1.0f / (float)C;

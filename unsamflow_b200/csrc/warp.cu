@@ -96,16 +96,19 @@ warp_fwd_kernel(const float *__restrict__ x, const float *__restrict__ flow, flo
     const float v = __ldg(flow + (size_t)b * 2 * HW + HW + rem);
     const Taps t = make_taps(y, xo, u, v, H, W, border, rcp);
     const float nw = t.ex * t.ey, ne = t.wx * t.ey, sw = t.ex * t.wy, se = t.wx * t.wy;
-    const float *xb = x + (size_t)b * C * HW;
-    float *ob = out + (size_t)b * C * HW + rem;
+    // two row pointers (taps nw/ne and sw/se are neighbours) bumped by one slice stride per channel:
+    // no per-tap address arithmetic in the loop; out-of-image taps are predicated off, never read
+    const size_t step = (size_t)NS * HW;
+    const float *p0 = x + ((size_t)b * C + cs) * HW + t.o_nw;
+    const float *p1 = p0 + W;
+    float *o = out + ((size_t)b * C + cs) * HW + rem;
 #pragma unroll 4
-    for (int c = cs; c < C; c += NS) {
-        const float *pl = xb + (size_t)c * HW;
-        float acc = ldp(pl, t.o_nw, t.k_nw) * nw;
-        acc = fmaf(ldp(pl, t.o_ne, t.k_ne), ne, acc);
-        acc = fmaf(ldp(pl, t.o_sw, t.k_sw), sw, acc);
-        acc = fmaf(ldp(pl, t.o_se, t.k_se), se, acc);
-        ob[(size_t)c * HW] = acc;
+    for (int c = cs; c < C; c += NS, p0 += step, p1 += step, o += step) {
+        float acc = (t.k_nw ? __ldg(p0) : 0.f) * nw;
+        acc = fmaf(t.k_ne ? __ldg(p0 + 1) : 0.f, ne, acc);
+        acc = fmaf(t.k_sw ? __ldg(p1) : 0.f, sw, acc);
+        acc = fmaf(t.k_se ? __ldg(p1 + 1) : 0.f, se, acc);
+        *o = acc;
     }
 }
 
@@ -185,26 +188,27 @@ warp_bwd_kernel(const float *__restrict__ x, const float *__restrict__ flow, con
             emit_tap(ws, b * HW, t.o_sw, t.k_sw, sw, rem);
             emit_tap(ws, b * HW, t.o_se, t.k_se, se, rem);
         }
-        const float *xb = x + (size_t)b * C * HW;
-        const float *gb = gout + (size_t)b * C * HW + rem;
-        float *gxb = (MODE == 2) ? gx + (size_t)b * C * HW : nullptr;
+        const size_t step = (size_t)NS * HW;
+        const float *gb = gout + ((size_t)b * C + cs) * HW + rem;
+        const float *p0 = x + ((size_t)b * C + cs) * HW + t.o_nw;
+        const float *p1 = p0 + W;
+        float *q0 = (MODE == 2) ? gx + ((size_t)b * C + cs) * HW + t.o_nw : nullptr;
         if (gflow != nullptr || MODE == 2) {
 #pragma unroll 4
-            for (int c = cs; c < C; c += NS) {
-                const float go = __ldg(gb + (size_t)c * HW);
+            for (int c = cs; c < C; c += NS, gb += step, p0 += step, p1 += step) {
+                const float go = __ldg(gb);
                 if (gflow != nullptr) {
-                    const float *plane = xb + (size_t)c * HW;
-                    const float vnw = ldp(plane, t.o_nw, t.k_nw), vne = ldp(plane, t.o_ne, t.k_ne);
-                    const float vsw = ldp(plane, t.o_sw, t.k_sw), vse = ldp(plane, t.o_se, t.k_se);
+                    const float vnw = t.k_nw ? __ldg(p0) : 0.f, vne = t.k_ne ? __ldg(p0 + 1) : 0.f;
+                    const float vsw = t.k_sw ? __ldg(p1) : 0.f, vse = t.k_se ? __ldg(p1 + 1) : 0.f;
                     gix = fmaf(go, fmaf(t.ey, vne - vnw, t.wy * (vse - vsw)), gix);
                     giy = fmaf(go, fmaf(t.ex, vsw - vnw, t.wx * (vse - vne)), giy);
                 }
                 if (MODE == 2) {
-                    float *plane = gxb + (size_t)c * HW;
-                    if (t.k_nw) atomicAdd(plane + t.o_nw, nw * go);
-                    if (t.k_ne) atomicAdd(plane + t.o_ne, ne * go);
-                    if (t.k_sw) atomicAdd(plane + t.o_sw, sw * go);
-                    if (t.k_se) atomicAdd(plane + t.o_se, se * go);
+                    if (t.k_nw) atomicAdd(q0, nw * go);
+                    if (t.k_ne) atomicAdd(q0 + 1, ne * go);
+                    if (t.k_sw) atomicAdd(q0 + W, sw * go);
+                    if (t.k_se) atomicAdd(q0 + W + 1, se * go);
+                    q0 += step;
                 }
             }
         }
@@ -272,16 +276,22 @@ warp_gx_gather(const float *__restrict__ gout, float *__restrict__ gx, Workspace
     USF_CS(2, 4); USF_CS(3, 5);
     USF_CS(3, 4);
 #undef USF_CS
-    const float *gb = gout + (size_t)b * C * HW;
-    float *ob = gx + (size_t)b * C * HW + rem;
+    const size_t step = (size_t)NS * HW;
+    const float *plane = gout + ((size_t)b * C + cs) * HW;
+    float *o = gx + ((size_t)b * C + cs) * HW + rem;
+    // most targets receive <= 4 taps (exactly 4 for a smooth flow): the upper half is a rarely taken branch
 #pragma unroll 2
-    for (int c = cs; c < C; c += NS) {
-        const float *plane = gb + (size_t)c * HW;
+    for (int c = cs; c < C; c += NS, plane += step, o += step) {
         float acc = 0.f;
 #pragma unroll
-        for (int i = 0; i < kSlots; ++i)
+        for (int i = 0; i < 4; ++i)
             if (i < n) acc = fmaf(w[i], __ldg(plane + src[i]), acc);
-        ob[(size_t)c * HW] = acc;
+        if (n > 4) {
+#pragma unroll
+            for (int i = 4; i < kSlots; ++i)
+                if (i < n) acc = fmaf(w[i], __ldg(plane + src[i]), acc);
+        }
+        *o = acc;
     }
 }
 
@@ -298,7 +308,13 @@ warp_gx_overflow(const float *__restrict__ gout, float *__restrict__ gx, Workspa
     }
 }
 
-int pick_ns(int C) { return C >= 32 ? 8 : C >= 16 ? 4 : C >= 8 ? 2 : 1; }
+// Channel slices per pixel: enough threads to fill the chip (~one full wave of 148 x 2048), but as few
+// slices as possible because every slice repeats the coordinate arithmetic (two IEEE divisions).
+int pick_ns(int C, int N) {
+    int ns = 1;
+    while (ns < 8 && (long)N * ns < 148L * 2048 && C >= 8 * ns) ns *= 2;
+    return ns;
+}
 
 }  // namespace
 
@@ -308,7 +324,7 @@ int warp_fwd_f32(const float *x, const float *flow, float *out, int B, int C, in
                  unsigned flags, cudaStream_t stream) {
     const int N = B * H * W;
     const int border = pad_mode == USF_PAD_BORDER, rcp = (flags & USF_FLAG_COORD_RECIPROCAL) ? 1 : 0;
-    const int ns = pick_ns(C);
+    const int ns = pick_ns(C, N);
     const int blocks = (N + kBlock / ns - 1) / (kBlock / ns);
 #define USF_LAUNCH(NS) warp_fwd_kernel<NS><<<blocks, kBlock, 0, stream>>>(x, flow, out, N, C, H, W, border, rcp)
     switch (ns) {
@@ -342,7 +358,7 @@ int warp_bwd_f32(const float *x, const float *flow, const float *gout, float *gx
                  cudaStream_t stream) {
     const int N = B * H * W, HW = H * W;
     const int border = pad_mode == USF_PAD_BORDER, rcp = (flags & USF_FLAG_COORD_RECIPROCAL) ? 1 : 0;
-    const int ns = pick_ns(C);
+    const int ns = pick_ns(C, N);
     const int blocks = (N + kBlock / ns - 1) / (kBlock / ns);
     Workspace ws = {};
     if (gx == nullptr) {
