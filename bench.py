@@ -76,14 +76,14 @@ def cpu_reference_step(B, H, W, flow_sigma, seed=42):
     for lvl, (C, h, w) in enumerate(levels):
         f1, f2 = torch.randn(B, C, h, w, generator=gen), torch.randn(B, C, h, w, generator=gen)
         for _ in range(2):  # two directions
-            fl = flow_sigma * torch.randn(B, 2, h, w, generator=gen)
+            fl = hotpath.synthetic_flow(B, h, w, flow_sigma, gen)
             go = torch.randn(B, 81, h, w, generator=gen)
             data.append(("model", lvl, f1, f2, fl, go))
             f1, f2 = f2, f1
     for (C, h, w) in scales:
         for _ in range(2):
             im = torch.rand(B, C, h, w, generator=gen)
-            fl = flow_sigma * torch.randn(B, 2, h, w, generator=gen)
+            fl = hotpath.synthetic_flow(B, h, w, flow_sigma, gen)
             go = torch.randn(B, C, h, w, generator=gen)
             data.append(("loss", 0, im, None, fl, go))
 
@@ -145,7 +145,9 @@ def workload_config(args, extra=None):
     cfg = {"workload": f"PWC-Lite kitti_base training-step hot path (corr+flow_warp fwd+bwd), synthetic "
                        f"{args.height}x{args.width} pairs, B={args.batch} per GPU",
            "batch_per_gpu": args.batch, "height": args.height, "width": args.width, "max_displacement": 4,
-           "flow_sigma_px": args.flow_sigma, "parallelism": f"dp{args.gpus} (batch replicas, no data-path collective)"}
+           "flow_sigma_px": args.flow_sigma,
+           "flow": "smooth synthetic flow: N(0,sigma^2) on an 8-px lattice, bilinear, + N(0,0.1^2) residual",
+           "parallelism": f"dp{args.gpus} (batch replicas, no data-path collective)"}
     if extra:
         cfg.update(extra)
     return cfg

@@ -12,12 +12,14 @@ import json
 import os
 import statistics
 import sys
+import time
 
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from unsamflow_b200 import hotpath, ops  # noqa: E402
 
+FLOW_KIND = "smooth"
 KITTI = ["8x192x4x13", "8x128x8x26", "8x96x16x52", "8x64x32x104", "8x32x64x208"]
 
 
@@ -34,7 +36,8 @@ def build(op, shape, sigma):
         go = torch.randn(B, 81, H, W, generator=g).to(dev)
         g1, g2 = torch.empty_like(x1), torch.empty_like(x2)
         return (lambda: ops.corr_bwd(x1, x2, go, gx1=g1, gx2=g2)), hotpath.corr_bwd_bytes(*shape), 2 * hotpath.corr_fwd_flops(*shape), 2
-    fl = (sigma * torch.randn(B, 2, H, W, generator=g)).to(dev)
+    fl = (hotpath.synthetic_flow(B, H, W, sigma, g) if FLOW_KIND == "smooth"
+          else sigma * torch.randn(B, 2, H, W, generator=g)).to(dev)
     if op == "warp_fwd":
         out = torch.empty_like(x1)
         return (lambda: ops.warp_fwd(x1, fl, "border", out=out)), hotpath.warp_fwd_bytes(*shape), 0, 1
@@ -60,8 +63,23 @@ def main():
     ap.add_argument("--cold", action="store_true")
     ap.add_argument("--sigma", type=float, default=3.0)
     ap.add_argument("--out", default="")
+    ap.add_argument("--flow", default="smooth", choices=["smooth", "iid"])
     args = ap.parse_args()
+    global FLOW_KIND
+    FLOW_KIND = args.flow
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    # wake the GPU up: a fresh box idles at ~120 MHz and takes a while to reach its boost clock
+    burn = torch.randn(4096, 4096, device="cuda")
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < 1.0:
+        burn @ burn
+    torch.cuda.synchronize()
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        nvh = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device())
+    except Exception:  # noqa: BLE001
+        pynvml, nvh = None, None
     inner = 1 if args.cold else args.inner
     rows = []
     for op in args.ops.split(","):
@@ -70,6 +88,8 @@ def main():
             fn, nbytes, flops, launches = build(op, shape, args.sigma)
             for _ in range(3):
                 fn()
+            for _ in range(20):
+                burn @ burn
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
@@ -84,9 +104,10 @@ def main():
                 b.synchronize()
                 ts.append(a.elapsed_time(b) * 1e3 / inner)
             us = statistics.median(ts)
+            mhz = pynvml.nvmlDeviceGetClockInfo(nvh, pynvml.NVML_CLOCK_SM) if nvh is not None else None
             row = {"op": op, "shape": s, "us": round(us, 2), "min_us": round(min(ts), 2), "launches": launches,
                    "GBps": round(nbytes / us / 1e3, 1), "TFLOPs": round(flops / us / 1e6, 2),
-                   "l2": "cold" if args.cold else "warm"}
+                   "l2": "cold" if args.cold else "warm", "sm_mhz": mhz}
             rows.append(row)
             print(json.dumps(row), flush=True)
     if args.out:

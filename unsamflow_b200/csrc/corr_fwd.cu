@@ -98,6 +98,24 @@ __device__ __forceinline__ void fma_channel(float (&acc)[kD][8], const float *__
         for (int i = 0; i < 8; ++i) acc[dx][i] = fmaf(a[i], w[dx + i], acc[dx][i]);
 }
 
+// Operands of one channel for one thread: x1 strip (8) + x2 window (16), as six 16-byte LDS.
+struct ChanOps {
+    float4 a0, a1, w0, w1, w2, w3;
+};
+__device__ __forceinline__ void load_ops(ChanOps &o, const float *__restrict__ p1, const float *__restrict__ p2) {
+    o.a0 = lds128(p1); o.a1 = lds128(p1 + 4);
+    o.w0 = lds128(p2); o.w1 = lds128(p2 + 4); o.w2 = lds128(p2 + 8); o.w3 = lds128(p2 + 12);
+}
+__device__ __forceinline__ void fma_ops(float (&acc)[kD][8], const ChanOps &o) {
+    const float a[8] = {o.a0.x, o.a0.y, o.a0.z, o.a0.w, o.a1.x, o.a1.y, o.a1.z, o.a1.w};
+    const float w[16] = {o.w0.x, o.w0.y, o.w0.z, o.w0.w, o.w1.x, o.w1.y, o.w1.z, o.w1.w,
+                         o.w2.x, o.w2.y, o.w2.z, o.w2.w, o.w3.x, o.w3.y, o.w3.z, o.w3.w};
+#pragma unroll
+    for (int dx = 0; dx < kD; ++dx)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[dx][i] = fmaf(a[i], w[dx + i], acc[dx][i]);
+}
+
 __device__ __forceinline__ float finish(float v, float rc, bool leaky, float slope) {
     v *= rc;
     return (leaky && v < 0.f) ? v * slope : v;
@@ -261,21 +279,64 @@ constexpr int TA_THREADS = 32 * (kD + 1);                  // 9 consumer warps +
 constexpr int X1_BYTES = CK * TH * X1S * 4;                // 9216  (box 36 x 8 x 8)
 constexpr int TA_X2_BYTES = CK * A_ROWS2 * X2S * 4;        // 22528 (box 44 x 16 x 8)
 constexpr int TA_STAGE_BYTES = X1_BYTES + TA_X2_BYTES;     // 31744
-constexpr int TA_SMEM = NST * TA_STAGE_BYTES;              // 95232
 
 // grid = (tiles_x, tiles_y, B)
+// Persistent tile kernel.  grid = min(#tiles, 148 * OCC) CTAs; CTA i walks tiles i, i+grid, ...
+// The producer lane streams stages continuously ACROSS tiles, so while the consumer warps finish a
+// tile (and its stores drain) the next tile's channels are already landing: per-tile start-up
+// latency (first TMA round trip, ~1 us) is paid once per CTA instead of once per tile.
+//   PIPE = false: 96 registers, 2 CTAs/SM (20 warps: the SM's four schedulers get 5 warps each);
+//   PIPE = true : software-pipelined operand loads (channel c+1 in flight under the FFMAs of c),
+//                 ~130 registers, 1 CTA/SM with a 6-stage ring; used when tiles <= 1.5 per SM.
+template <bool PIPE> struct T9Cfg {
+    static constexpr int kStages = PIPE ? 6 : 3;
+    static constexpr int kMinBlocks = PIPE ? 1 : 2;
+    static constexpr int kSmem = kStages * TA_STAGE_BYTES + 2 * kStages * 8;
+};
+
+// Store 8 consecutive pixels x 9 dx of one row so that every STG.128 fills whole 32-byte sectors:
+// lanes (r,q) and (r^1,q) swap halves, then one instruction writes both 16-byte halves of a sector.
 template <bool LEAKY>
-__global__ void __launch_bounds__(TA_THREADS, 2)
+__device__ __forceinline__ void store_tile(float (&acc)[kD][8], float *__restrict__ out, int b, int dyi, int y0,
+                                           int x0, int r, int q, int H, int W, float rc, float slope) {
+    const bool odd = r & 1;
+    const int row0 = y0 + (r & ~1), gx = x0 + 8 * q + (odd ? 4 : 0);
+    const size_t kstride = (size_t)H * W;
+    float *o = out + (((size_t)b * kK + dyi * kD) * H + row0) * W + gx;
+    const bool c_ok = gx < W, r0_ok = row0 < H, r1_ok = row0 + 1 < H;
+#pragma unroll
+    for (int dx = 0; dx < kD; ++dx, o += kstride) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = finish_t<LEAKY>(acc[dx][i], rc, slope);
+        float snd[4], rcv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) snd[i] = odd ? v[i] : v[4 + i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rcv[i] = __shfl_xor_sync(0xffffffffu, snd[i], 4);
+        // even lane: (row0, own low half) then (row0+1, partner's low half)
+        // odd  lane: (row0, partner's high half) then (row0+1, own high half)
+        const float4 first = odd ? make_float4(rcv[0], rcv[1], rcv[2], rcv[3]) : make_float4(v[0], v[1], v[2], v[3]);
+        const float4 second = odd ? make_float4(v[4], v[5], v[6], v[7]) : make_float4(rcv[0], rcv[1], rcv[2], rcv[3]);
+        if (c_ok && r0_ok) *reinterpret_cast<float4 *>(o) = first;
+        if (c_ok && r1_ok) *reinterpret_cast<float4 *>(o + W) = second;
+    }
+}
+
+template <bool LEAKY, bool PIPE>
+__global__ void __launch_bounds__(TA_THREADS, T9Cfg<PIPE>::kMinBlocks)
 corr_fwd_tile9_tma(const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
-                   float *__restrict__ out, int C, int H, int W, float rc, float slope) {
+                   float *__restrict__ out, int C, int H, int W, int tiles_x, int tiles_y, int ntiles, float rc,
+                   float slope) {
+    constexpr int NS = T9Cfg<PIPE>::kStages;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[NST], empty_bar[NST];
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + NS * TA_STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + NS;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
     const int nchunk = (C + CK - 1) / CK;
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NST; ++s) {
+        for (int s = 0; s < NS; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], kD);
         }
@@ -283,55 +344,60 @@ corr_fwd_tile9_tma(const __grid_constant__ CUtensorMap m1, const __grid_constant
     }
     __syncthreads();
 
-    if (warp == kD) {  // producer warp: one lane feeds the ring
+    if (warp == kD) {  // producer warp: one lane feeds the ring, running ahead across tiles
         if (lane == 0) {
             tma_prefetch_desc(&m1);
             tma_prefetch_desc(&m2);
-            for (int k = 0; k < nchunk; ++k) {
-                const int s = k % NST;
-                if (k >= NST) mbar_wait(&empty_bar[s], ((k / NST) - 1) & 1);
-                unsigned char *st = smem_raw + s * TA_STAGE_BYTES;
-                mbar_expect_tx(&full_bar[s], TA_STAGE_BYTES);
-                tma_load_4d(st, &m1, &full_bar[s], x0, y0, k * CK, b);
-                tma_load_4d(st + X1_BYTES, &m2, &full_bar[s], x0 - kMaxDisp, y0 - kMaxDisp, k * CK, b);
+            int it = 0;
+            for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+                const int x0 = tx * TW, y0 = ty * TH;
+                for (int k = 0; k < nchunk; ++k, ++it) {
+                    const int s = it % NS;
+                    if (it >= NS) mbar_wait(&empty_bar[s], ((it / NS) - 1) & 1);
+                    unsigned char *st = smem_raw + s * TA_STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[s], TA_STAGE_BYTES);
+                    tma_load_4d(st, &m1, &full_bar[s], x0, y0, k * CK, b);
+                    tma_load_4d(st + X1_BYTES, &m2, &full_bar[s], x0 - kMaxDisp, y0 - kMaxDisp, k * CK, b);
+                }
             }
         }
         return;
     }
 
     const int r = lane >> 2, q = lane & 3;
-    float acc[kD][8];
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int tx = t % tiles_x, ty = (t / tiles_x) % tiles_y, b = t / (tiles_x * tiles_y);
+        float acc[kD][8];
 #pragma unroll
-    for (int dx = 0; dx < kD; ++dx)
+        for (int dx = 0; dx < kD; ++dx)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[dx][i] = 0.f;
+            for (int i = 0; i < 8; ++i) acc[dx][i] = 0.f;
 
-    for (int k = 0; k < nchunk; ++k) {
-        const int s = k % NST;
-        mbar_wait(&full_bar[s], (k / NST) & 1);
-        const float *st = reinterpret_cast<const float *>(smem_raw + s * TA_STAGE_BYTES);
-        const float *p1 = st + r * X1S + 8 * q;
-        const float *p2 = st + CK * TH * X1S + (r + warp) * X2S + 8 * q;
+        for (int k = 0; k < nchunk; ++k, ++it) {
+            const int s = it % NS;
+            mbar_wait(&full_bar[s], (it / NS) & 1);
+            const float *st = reinterpret_cast<const float *>(smem_raw + s * TA_STAGE_BYTES);
+            const float *p1 = st + r * X1S + 8 * q;
+            const float *p2 = st + CK * TH * X1S + (r + warp) * X2S + 8 * q;
+            if (PIPE) {
+                ChanOps cur, nxt;
+                load_ops(cur, p1, p2);
+#pragma unroll
+                for (int c = 0; c < CK; ++c) {
+                    if (c + 1 < CK) load_ops(nxt, p1 + (c + 1) * TH * X1S, p2 + (c + 1) * A_ROWS2 * X2S);
+                    fma_ops(acc, cur);
+                    if (c + 1 < CK) cur = nxt;
+                }
+            } else {
 #pragma unroll 2
-        for (int c = 0; c < CK; ++c) fma_channel(acc, p1 + c * TH * X1S, p2 + c * A_ROWS2 * X2S);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
-    }
-
-    const int gy = y0 + r, gx = x0 + 8 * q;
-    if (gy >= H) return;
-    float *o = out + (((size_t)b * kK + warp * kD) * H + gy) * W + gx;
-    const size_t kstride = (size_t)H * W;
-#pragma unroll
-    for (int dx = 0; dx < kD; ++dx, o += kstride) {
-        if (gx < W)
-            *reinterpret_cast<float4 *>(o) =
-                make_float4(finish_t<LEAKY>(acc[dx][0], rc, slope), finish_t<LEAKY>(acc[dx][1], rc, slope),
-                            finish_t<LEAKY>(acc[dx][2], rc, slope), finish_t<LEAKY>(acc[dx][3], rc, slope));
-        if (gx + 4 < W)
-            *reinterpret_cast<float4 *>(o + 4) =
-                make_float4(finish_t<LEAKY>(acc[dx][4], rc, slope), finish_t<LEAKY>(acc[dx][5], rc, slope),
-                            finish_t<LEAKY>(acc[dx][6], rc, slope), finish_t<LEAKY>(acc[dx][7], rc, slope));
+                for (int c = 0; c < CK; ++c) fma_channel(acc, p1 + c * TH * X1S, p2 + c * A_ROWS2 * X2S);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        }
+        store_tile<LEAKY>(acc, out, b, warp, ty * TH, tx * TW, r, q, H, W, rc, slope);
     }
 }
 
@@ -434,9 +500,20 @@ cudaError_t launch_tma(bool splitc, const CUtensorMap &m1, const CUtensorMap &m2
         if (once != cudaSuccess) return once;
         corr_fwd_splitc_tma<LEAKY><<<dim3(tx, ty, B * kD), TB_THREADS, TB_SMEM, stream>>>(m1, m2b, out, C, H, W, rc, slope);
     } else {
-        static cudaError_t once = prep(corr_fwd_tile9_tma<LEAKY>, TA_SMEM);
-        if (once != cudaSuccess) return once;
-        corr_fwd_tile9_tma<LEAKY><<<dim3(tx, ty, B), TA_THREADS, TA_SMEM, stream>>>(m1, m2a, out, C, H, W, rc, slope);
+        const int ntiles = tx * ty * B;
+        if (ntiles * 2 <= 3 * 148) {  // at most 1.5 tiles per SM: one pipelined CTA per SM
+            static cudaError_t once = prep(corr_fwd_tile9_tma<LEAKY, true>, T9Cfg<true>::kSmem);
+            if (once != cudaSuccess) return once;
+            const int grid = ntiles < 148 ? ntiles : 148;
+            corr_fwd_tile9_tma<LEAKY, true><<<grid, TA_THREADS, T9Cfg<true>::kSmem, stream>>>(
+                m1, m2a, out, C, H, W, tx, ty, ntiles, rc, slope);
+        } else {
+            static cudaError_t once = prep(corr_fwd_tile9_tma<LEAKY, false>, T9Cfg<false>::kSmem);
+            if (once != cudaSuccess) return once;
+            const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;
+            corr_fwd_tile9_tma<LEAKY, false><<<grid, TA_THREADS, T9Cfg<false>::kSmem, stream>>>(
+                m1, m2a, out, C, H, W, tx, ty, ntiles, rc, slope);
+        }
     }
     return cudaGetLastError();
 }
@@ -460,7 +537,8 @@ int corr_fwd_f32(const float *x1, const float *x2, float *out, int B, int C, int
     const int leaky = (flags & USF_FLAG_LEAKY_RELU) ? 1 : 0;
     // Few tiles and many channels: split dy over CTAs and channels over warps.
     const long tiles = (long)tx * ty * B;
-    const bool splitc = tiles < 2 * 148 && C >= 48;
+    // fewer tiles than half the SMs: split dy over CTAs and channels over warps; else persistent tiles
+    const bool splitc = tiles * 2 < 148 && C >= 48;
     if (vec) {
         // TMA path: tensor maps are encoded on the host per call (pointers differ per call) and travel
         // as __grid_constant__ kernel parameters; nothing is cached between calls (re-entrant).

@@ -27,6 +27,20 @@ NUM_LOSS_SCALES = 4                        # w_ph_scales [1,1,1,1,0], configs/ki
 K = ops.NUM_DISPLACEMENTS
 
 
+def synthetic_flow(B, h, w, sigma, gen, fine_sigma=0.1, cell=8):
+    """Seeded synthetic flow with the spatial statistics of a real one: optical flow is piecewise
+    smooth (PWC-Lite itself produces each level by bilinear x2 upsampling of the coarser flow plus a
+    small residual, models/pwclite.py:299-301,368-371).  Coarse N(0, sigma^2) vectors on a `cell`-pixel
+    lattice, bilinearly interpolated, plus N(0, fine_sigma^2) per-pixel residual.  (White-noise flow,
+    as used in the parity tests, scatters every warp's taps over ~20 cache sectors and measures the
+    gather hardware, not the kernel.)"""
+    import torch.nn.functional as F
+    ch, cw = (h + cell - 1) // cell + 1, (w + cell - 1) // cell + 1
+    coarse = torch.randn(B, 2, ch, cw, generator=gen) * sigma
+    flow = F.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=True)
+    return flow + fine_sigma * torch.randn(B, 2, h, w, generator=gen)
+
+
 def conv_out(n):
     """3x3 stride-2 pad-1 conv output size (models/pwclite.py:59-63)."""
     return (n - 1) // 2 + 1
@@ -84,13 +98,19 @@ class OpRecord:
 class HotPathStep:
     """Preallocated synthetic inputs/outputs + the ordered op list of one training step."""
 
-    def __init__(self, B, H, W, device="cuda", seed=42, flow_sigma=3.0, pad="border"):
+    def __init__(self, B, H, W, device="cuda", seed=42, flow_sigma=3.0, pad="border", flow_kind="smooth"):
         self.B, self.H, self.W, self.pad = B, H, W, pad
+        self.flow_kind = flow_kind
         self.device = torch.device(device)
         gen = torch.Generator(device="cpu").manual_seed(seed)
 
         def randn(*shape, scale=1.0):
             return (torch.randn(*shape, generator=gen) * scale).to(self.device)
+
+        def flow(h, w):
+            if flow_kind == "smooth":
+                return synthetic_flow(B, h, w, flow_sigma, gen).to(self.device)
+            return randn(B, 2, h, w, scale=flow_sigma)  # "iid": white noise, worst case for the gathers
 
         self.levels = pyramid_shapes(H, W)
         self.scales = loss_shapes(H, W)
@@ -102,7 +122,7 @@ class HotPathStep:
                 self.input_names.append(f"{n}.L{lvl}")
             for d in ("d12", "d21"):
                 if lvl > 0:
-                    t[f"flow.L{lvl}.{d}"] = randn(B, 2, h, w, scale=flow_sigma)
+                    t[f"flow.L{lvl}.{d}"] = flow(h, w)
                     t[f"x2w.L{lvl}.{d}"] = torch.empty(B, C, h, w, device=self.device)
                     t[f"gfeat2.L{lvl}.{d}"] = torch.empty(B, C, h, w, device=self.device)
                     t[f"gflow.L{lvl}.{d}"] = torch.empty(B, 2, h, w, device=self.device)
@@ -119,7 +139,7 @@ class HotPathStep:
                 t[f"{n}.S{s}"] = torch.rand(B, C, h, w, generator=gen).to(self.device)
                 self.input_names.append(f"{n}.S{s}")
             for d in ("d12", "d21"):
-                t[f"lflow.S{s}.{d}"] = randn(B, 2, h, w, scale=flow_sigma)
+                t[f"lflow.S{s}.{d}"] = flow(h, w)
                 t[f"recons.S{s}.{d}"] = torch.empty(B, C, h, w, device=self.device)
                 t[f"grecons.S{s}.{d}"] = randn(B, C, h, w)
                 t[f"glflow.S{s}.{d}"] = torch.empty(B, 2, h, w, device=self.device)
