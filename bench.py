@@ -146,7 +146,7 @@ def workload_config(args, extra=None):
                        f"{args.height}x{args.width} pairs, B={args.batch} per GPU",
            "batch_per_gpu": args.batch, "height": args.height, "width": args.width, "max_displacement": 4,
            "flow_sigma_px": args.flow_sigma,
-           "flow": "smooth synthetic flow: N(0,sigma^2) on an 8-px lattice, bilinear, + N(0,0.1^2) residual",
+           "flow": "smooth synthetic flow: N(0,sigma^2) on a 24-px lattice, bilinear, + N(0,0.05^2) residual",
            "parallelism": f"dp{args.gpus} (batch replicas, no data-path collective)"}
     if extra:
         cfg.update(extra)
@@ -242,8 +242,7 @@ def run_ours(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
     # ---- per-op table (also picks the dominant op) ------------------------------------------------
-    for op in step.ops:
-        op.fn()
+    step.measure_launches()
     torch.cuda.synchronize()
     table = []
     for op in step.ops:

@@ -245,17 +245,16 @@ struct GLoader<GX2, kD> {
 // mx: box [8ch][16][44] over the feature map.  mg over gout: gx1 box [9ch][8][36], gx2 box [9ch][8][44].
 // grid = (tiles_x, tiles_y, B * ngroups)
 template <bool GX2>
-__global__ void __launch_bounds__(T_THREADS, 2)
-corr_bwd_gather_tma(const __grid_constant__ CUtensorMap mx, const __grid_constant__ CUtensorMap mg,
-                    float *__restrict__ gx, int C, int H, int W, int ngroups, float rc) {
-    extern __shared__ __align__(1024) unsigned char smem_raw[];
+__device__ __forceinline__ void bwd_tile(unsigned char *smem_raw, const CUtensorMap &mx, const CUtensorMap &mg,
+                                         float *__restrict__ gx, int C, int H, int W, int ngroups, int zidx,
+                                         float rc) {
     constexpr int GB = GTile<GX2>::kBytes;
     unsigned char *gbase = smem_raw + NCW * XW_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(gbase + 2 * GB);
     uint64_t *xfull = bars, *gfull = bars + NCW, *gempty = bars + NCW + 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-    const int b = blockIdx.z / ngroups, cg = blockIdx.z - b * ngroups;
+    const int b = zidx / ngroups, cg = zidx - b * ngroups;
     const int c0 = cg * CG;
     if (tid == 0) {
 #pragma unroll
@@ -342,20 +341,41 @@ corr_bwd_gather_tma(const __grid_constant__ CUtensorMap mx, const __grid_constan
     }
 }
 
-template <bool GX2>
-cudaError_t launch_tma(const CUtensorMap &mx, const CUtensorMap &mg, float *gx, int B, int C, int H, int W,
+// ONE launch computes both gradients: blockIdx.z selects (gradient, batch item, channel group).  The
+// gx1 and gx2 halves of the grid are independent, so the fused grid packs the SMs better than two
+// back-to-back launches (twice the CTAs per wave tail) and saves a launch.
+// z layout: [0, nz) -> first requested gradient, [nz, 2 nz) -> gx2 when both are requested.
+__global__ void __launch_bounds__(T_THREADS, 2)
+corr_bwd_gather_tma(const __grid_constant__ CUtensorMap mx1, const __grid_constant__ CUtensorMap mg1,
+                    const __grid_constant__ CUtensorMap mx2, const __grid_constant__ CUtensorMap mg2,
+                    float *__restrict__ gx1, float *__restrict__ gx2, int C, int H, int W, int ngroups, int nz,
+                    float rc) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    int z = blockIdx.z;
+    const bool second = (gx1 == nullptr) || z >= nz;
+    if (z >= nz) z -= nz;
+    if (second)
+        bwd_tile<true>(smem_raw, mx2, mg2, gx2, C, H, W, ngroups, z, rc);
+    else
+        bwd_tile<false>(smem_raw, mx1, mg1, gx1, C, H, W, ngroups, z, rc);
+}
+
+cudaError_t launch_tma(const CUtensorMap &mx1, const CUtensorMap &mg1, const CUtensorMap &mx2,
+                       const CUtensorMap &mg2, float *gx1, float *gx2, int B, int C, int H, int W,
                        cudaStream_t stream) {
-    constexpr int SM = GTile<GX2>::kSmem;
+    constexpr int SM = GTile<true>::kSmem > GTile<false>::kSmem ? GTile<true>::kSmem : GTile<false>::kSmem;
     static cudaError_t once = [] {
-        cudaError_t e = cudaFuncSetAttribute(corr_bwd_gather_tma<GX2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
+        cudaError_t e = cudaFuncSetAttribute(corr_bwd_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
         if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(corr_bwd_gather_tma<GX2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        return cudaFuncSetAttribute(corr_bwd_gather_tma, cudaFuncAttributePreferredSharedMemoryCarveout,
                                     cudaSharedmemCarveoutMaxShared);
     }();
     if (once != cudaSuccess) return once;
     const int ngroups = (C + CG - 1) / CG;
-    dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B * ngroups);
-    corr_bwd_gather_tma<GX2><<<grid, T_THREADS, SM, stream>>>(mx, mg, gx, C, H, W, ngroups, 1.0f / (float)C);
+    const int nz = B * ngroups;
+    dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, nz * ((gx1 && gx2) ? 2 : 1));
+    corr_bwd_gather_tma<<<grid, T_THREADS, SM, stream>>>(mx1, mg1, mx2, mg2, gx1, gx2, C, H, W, ngroups, nz,
+                                                         1.0f / (float)C);
     return cudaGetLastError();
 }
 
@@ -385,21 +405,16 @@ int corr_bwd_f32(const float *x1, const float *x2, const float *gout, float *gx1
     int st = USF_OK;
     if (vec) {
         // TMA path (tensor maps encoded per call, passed as __grid_constant__ parameters)
-        CUtensorMap mx, mg;
+        CUtensorMap mx1, mg1, mx2, mg2;
         bool ok = true;
-        if (gx1) {
-            ok = make_nchw_map(&mx, x2, B, C, H, W, XS, XR, CT) && make_nchw_map(&mg, gout, B, kK, H, W, GS, TH, kD);
-            if (ok) {
-                st = note_launch(launch_tma<false>(mx, mg, gx1, B, C, H, W, stream));
-                if (st != USF_OK) return st;
-            }
+        if (gx1) ok = make_nchw_map(&mx1, x2, B, C, H, W, XS, XR, CT) && make_nchw_map(&mg1, gout, B, kK, H, W, GS, TH, kD);
+        if (ok && gx2) ok = make_nchw_map(&mx2, x1, B, C, H, W, XS, XR, CT) && make_nchw_map(&mg2, gout, B, kK, H, W, XS, TH, kD);
+        if (ok) {
+            if (!gx1) { mx1 = mx2; mg1 = mg2; }
+            if (!gx2) { mx2 = mx1; mg2 = mg1; }
+            return note_launch(launch_tma(mx1, mg1, mx2, mg2, gx1, gx2, B, C, H, W, stream));
         }
-        if (ok && gx2) {
-            ok = make_nchw_map(&mx, x1, B, C, H, W, XS, XR, CT) && make_nchw_map(&mg, gout, B, kK, H, W, XS, TH, kD);
-            if (ok) return note_launch(launch_tma<true>(mx, mg, gx2, B, C, H, W, stream));
-        }
-        if (ok) return st;
-        // encoding failed (driver entry point missing): fall through to the cp.async kernels
+        // encoding failed (driver entry point missing / TMA disabled): fall through to the cp.async kernels
     }
     if (gx1) {
         cudaError_t e = vec ? launch<false, true>(x2, gout, gx1, B, C, H, W, stream)

@@ -4,77 +4,123 @@
 // 52..208 pixels per image: the whole problem fits in L1/L2, has odd widths (no TMA, no 16-byte
 // vectors) and is pure launch/latency.  Tiling through shared memory only adds barriers there,
 // so these kernels read global memory directly (coalesced along x, everything L1/L2 resident):
-//   fwd:  one thread per output element (b,k,y,x), serial sum over channels, 8-way unrolled.
-//   bwd:  one thread per input element (b,c,y,x) computes BOTH gradients as 81-term gathers.
+//   fwd:  32 outputs x 8 channel slices per CTA (one warp per slice), partial sums reduced in a fixed
+//         order through shared memory: short dependent-load chains, plenty of threads.
+//   bwd:  one thread = 4 channels of one pixel x 3 displacement rows, BOTH gradients as gathers.
 // Same formulas as corr_fwd.cu / corr_bwd.cu (models/correlation_native.py:13-23).
 #include "common.cuh"
 
 namespace usf {
 namespace {
 
-constexpr int kThreads = 256;
+// ---- forward: 32 outputs x 8 channel slices per CTA, fixed-order reduction through shared memory ----
+constexpr int kFwdOutputs = 32, kFwdSlices = 8, kFwdThreads = kFwdOutputs * kFwdSlices;
 
 template <bool LEAKY>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kFwdThreads)
 corr_fwd_direct(const float *__restrict__ x1, const float *__restrict__ x2, float *__restrict__ out, int total,
                 int C, int H, int W, float rc, float slope) {
-    const int idx = blockIdx.x * kThreads + threadIdx.x;
-    if (idx >= total) return;
+    __shared__ float red[kFwdSlices][kFwdOutputs];
+    const int lane = threadIdx.x & 31, cs = threadIdx.x >> 5;  // one warp == one channel slice
+    const int idx = blockIdx.x * kFwdOutputs + lane;
     const int HW = H * W;
-    const int x = idx % W, y = (idx / W) % H, k = (idx / HW) % kK, b = idx / (HW * kK);
-    const int dy = k / kD - kMaxDisp, dx = k % kD - kMaxDisp;
-    const int yy = y + dy, xx = x + dx;
     float acc = 0.f;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
-        const float *p1 = x1 + (size_t)b * C * HW + y * W + x;
-        const float *p2 = x2 + (size_t)b * C * HW + yy * W + xx;
-        float a[4] = {0.f, 0.f, 0.f, 0.f};
-        int c = 0;
-        for (; c + 8 <= C; c += 8) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) a[u & 3] = fmaf(__ldg(p1 + (size_t)(c + u) * HW), __ldg(p2 + (size_t)(c + u) * HW), a[u & 3]);
+    if (idx < total) {
+        const int x = idx % W, y = (idx / W) % H, k = (idx / HW) % kK, b = idx / (HW * kK);
+        const int yy = y + k / kD - kMaxDisp, xx = x + k % kD - kMaxDisp;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+            const size_t step = (size_t)kFwdSlices * HW;
+            const float *p1 = x1 + ((size_t)b * C + cs) * HW + y * W + x;
+            const float *p2 = x2 + ((size_t)b * C + cs) * HW + yy * W + xx;
+            float a0 = 0.f, a1 = 0.f;
+            int c = cs;
+            for (; c + 3 * kFwdSlices < C; c += 4 * kFwdSlices, p1 += 4 * step, p2 += 4 * step) {
+                const float u0 = __ldg(p1), v0 = __ldg(p2), u1 = __ldg(p1 + step), v1 = __ldg(p2 + step);
+                const float u2 = __ldg(p1 + 2 * step), v2 = __ldg(p2 + 2 * step);
+                const float u3 = __ldg(p1 + 3 * step), v3 = __ldg(p2 + 3 * step);
+                a0 = fmaf(u0, v0, a0); a1 = fmaf(u1, v1, a1); a0 = fmaf(u2, v2, a0); a1 = fmaf(u3, v3, a1);
+            }
+            for (; c < C; c += kFwdSlices, p1 += step, p2 += step) a0 = fmaf(__ldg(p1), __ldg(p2), a0);
+            acc = a0 + a1;
         }
-        for (; c < C; ++c) a[0] = fmaf(__ldg(p1 + (size_t)c * HW), __ldg(p2 + (size_t)c * HW), a[0]);
-        acc = (a[0] + a[1]) + (a[2] + a[3]);
     }
-    float v = acc * rc;
+    red[cs][lane] = acc;
+    __syncthreads();
+    if (cs != 0 || idx >= total) return;
+    float sum = red[0][lane];
+#pragma unroll
+    for (int s = 1; s < kFwdSlices; ++s) sum += red[s][lane];
+    float v = sum * rc;
     if (LEAKY) v = v < 0.f ? v * slope : v;
     out[idx] = v;
 }
 
+// ---- backward: one thread = 4 channels of one pixel x one third of the displacement rows ----------
+// gO[k,y,x] and gO[k,y-dy,x-dx] are loaded once and reused for 4 channels (10 loads per 8 FFMA);
+// the 3 row-slices of a pixel live in different warps and are summed through shared memory.
+constexpr int kBwdItems = 64, kBwdSlices = 3, kBwdThreads = kBwdItems * kBwdSlices, kCC = 4;
+
 template <bool G1, bool G2>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kBwdThreads)
 corr_bwd_direct(const float *__restrict__ x1, const float *__restrict__ x2, const float *__restrict__ gout,
-                float *__restrict__ gx1, float *__restrict__ gx2, int total, int C, int H, int W, float rc) {
-    const int idx = blockIdx.x * kThreads + threadIdx.x;
-    if (idx >= total) return;
-    const int HW = H * W;
-    const int x = idx % W, y = (idx / W) % H, c = (idx / HW) % C, b = idx / (HW * C);
-    const float *pg = gout + (size_t)b * kK * HW;
-    const float *p1 = x1 + ((size_t)b * C + c) * HW;
-    const float *p2 = x2 + ((size_t)b * C + c) * HW;
-    float a1 = 0.f, a2 = 0.f;
+                float *__restrict__ gx1, float *__restrict__ gx2, int items, int C, int H, int W, float rc) {
+    __shared__ float red[kBwdSlices][2 * kCC][kBwdItems];
+    const int li = threadIdx.x % kBwdItems, ks = threadIdx.x / kBwdItems;
+    const int item = blockIdx.x * kBwdItems + li;
+    const int HW = H * W, CG = (C + kCC - 1) / kCC;
+    float a1[kCC] = {0.f, 0.f, 0.f, 0.f}, a2[kCC] = {0.f, 0.f, 0.f, 0.f};
+    int x = 0, y = 0, c0 = 0, b = 0;
+    if (item < items) {
+        x = item % W; y = (item / W) % H; c0 = ((item / HW) % CG) * kCC; b = item / (HW * CG);
+        const float *pg = gout + (size_t)b * kK * HW;
+        const float *p1 = x1 + ((size_t)b * C + c0) * HW;
+        const float *p2 = x2 + ((size_t)b * C + c0) * HW;
+        const int nc = min(kCC, C - c0);
 #pragma unroll 1
-    for (int dyi = 0; dyi < kD; ++dyi) {
-        const int dy = dyi - kMaxDisp;
-        const int yp = y + dy, ym = y - dy;
+        for (int dyi = 3 * ks; dyi < 3 * ks + 3; ++dyi) {
+            const int dy = dyi - kMaxDisp, yp = y + dy, ym = y - dy;
+            const bool ypok = yp >= 0 && yp < H, ymok = ym >= 0 && ym < H;
 #pragma unroll
-        for (int dxi = 0; dxi < kD; ++dxi) {
-            const int dx = dxi - kMaxDisp, k = dyi * kD + dxi;
-            if (G1) {
-                const int xp = x + dx;
-                if (yp >= 0 && yp < H && xp >= 0 && xp < W)
-                    a1 = fmaf(__ldg(pg + (size_t)k * HW + y * W + x), __ldg(p2 + yp * W + xp), a1);
-            }
-            if (G2) {
-                const int xm = x - dx;
-                if (ym >= 0 && ym < H && xm >= 0 && xm < W)
-                    a2 = fmaf(__ldg(pg + (size_t)k * HW + ym * W + xm), __ldg(p1 + ym * W + xm), a2);
+            for (int dxi = 0; dxi < kD; ++dxi) {
+                const int dx = dxi - kMaxDisp, k = dyi * kD + dxi;
+                if (G1) {
+                    const int xp = x + dx;
+                    if (ypok && xp >= 0 && xp < W) {
+                        const float g = __ldg(pg + (size_t)k * HW + y * W + x);
+                        const float *q = p2 + yp * W + xp;
+#pragma unroll
+                        for (int cc = 0; cc < kCC; ++cc)
+                            if (cc < nc) a1[cc] = fmaf(g, __ldg(q + (size_t)cc * HW), a1[cc]);
+                    }
+                }
+                if (G2) {
+                    const int xm = x - dx;
+                    if (ymok && xm >= 0 && xm < W) {
+                        const float g = __ldg(pg + (size_t)k * HW + ym * W + xm);
+                        const float *q = p1 + ym * W + xm;
+#pragma unroll
+                        for (int cc = 0; cc < kCC; ++cc)
+                            if (cc < nc) a2[cc] = fmaf(g, __ldg(q + (size_t)cc * HW), a2[cc]);
+                    }
+                }
             }
         }
     }
-    if (G1) gx1[idx] = a1 * rc;
-    if (G2) gx2[idx] = a2 * rc;
+#pragma unroll
+    for (int cc = 0; cc < kCC; ++cc) {
+        red[ks][cc][li] = a1[cc];
+        red[ks][kCC + cc][li] = a2[cc];
+    }
+    __syncthreads();
+    if (ks != 0 || item >= items) return;
+    const int nc = min(kCC, C - c0);
+    const size_t o = ((size_t)b * C + c0) * HW + y * W + x;
+#pragma unroll
+    for (int cc = 0; cc < kCC; ++cc) {
+        if (cc >= nc) break;
+        if (G1) gx1[o + (size_t)cc * HW] = ((red[0][cc][li] + red[1][cc][li]) + red[2][cc][li]) * rc;
+        if (G2) gx2[o + (size_t)cc * HW] = ((red[0][kCC + cc][li] + red[1][kCC + cc][li]) + red[2][kCC + cc][li]) * rc;
+    }
 }
 
 }  // namespace
@@ -82,26 +128,26 @@ corr_bwd_direct(const float *__restrict__ x1, const float *__restrict__ x2, cons
 int corr_fwd_direct_f32(const float *x1, const float *x2, float *out, int B, int C, int H, int W, unsigned flags,
                         float slope, cudaStream_t stream) {
     const int total = B * kK * H * W;
-    const int blocks = (total + kThreads - 1) / kThreads;
+    const int blocks = (total + kFwdOutputs - 1) / kFwdOutputs;
     const float rc = 1.0f / (float)C;
     if (flags & USF_FLAG_LEAKY_RELU)
-        corr_fwd_direct<true><<<blocks, kThreads, 0, stream>>>(x1, x2, out, total, C, H, W, rc, slope);
+        corr_fwd_direct<true><<<blocks, kFwdThreads, 0, stream>>>(x1, x2, out, total, C, H, W, rc, slope);
     else
-        corr_fwd_direct<false><<<blocks, kThreads, 0, stream>>>(x1, x2, out, total, C, H, W, rc, slope);
+        corr_fwd_direct<false><<<blocks, kFwdThreads, 0, stream>>>(x1, x2, out, total, C, H, W, rc, slope);
     return note_launch(cudaGetLastError());
 }
 
 int corr_bwd_direct_f32(const float *x1, const float *x2, const float *gout, float *gx1, float *gx2, int B, int C,
                         int H, int W, cudaStream_t stream) {
-    const int total = B * C * H * W;
-    const int blocks = (total + kThreads - 1) / kThreads;
+    const int items = B * ((C + kCC - 1) / kCC) * H * W;
+    const int blocks = (items + kBwdItems - 1) / kBwdItems;
     const float rc = 1.0f / (float)C;
     if (gx1 && gx2)
-        corr_bwd_direct<true, true><<<blocks, kThreads, 0, stream>>>(x1, x2, gout, gx1, gx2, total, C, H, W, rc);
+        corr_bwd_direct<true, true><<<blocks, kBwdThreads, 0, stream>>>(x1, x2, gout, gx1, gx2, items, C, H, W, rc);
     else if (gx1)
-        corr_bwd_direct<true, false><<<blocks, kThreads, 0, stream>>>(x1, x2, gout, gx1, gx2, total, C, H, W, rc);
+        corr_bwd_direct<true, false><<<blocks, kBwdThreads, 0, stream>>>(x1, x2, gout, gx1, gx2, items, C, H, W, rc);
     else
-        corr_bwd_direct<false, true><<<blocks, kThreads, 0, stream>>>(x1, x2, gout, gx1, gx2, total, C, H, W, rc);
+        corr_bwd_direct<false, true><<<blocks, kBwdThreads, 0, stream>>>(x1, x2, gout, gx1, gx2, items, C, H, W, rc);
     return note_launch(cudaGetLastError());
 }
 

@@ -249,38 +249,66 @@ template <int NS>
 __global__ void __launch_bounds__(kBlock)
 warp_gx_gather(const float *__restrict__ gout, float *__restrict__ gx, Workspace ws, int N, int C, int HW) {
     constexpr int PPB = kBlock / NS;
-    const int p = blockIdx.x * PPB + (threadIdx.x % PPB);
+    // slice 0 of every pixel loads and sorts the tap list once; the other slices read it from here
+    __shared__ int s_src[NS > 1 ? kSlots : 1][NS > 1 ? PPB : 1];
+    __shared__ float s_w[NS > 1 ? kSlots : 1][NS > 1 ? PPB : 1];
+    __shared__ int s_n[NS > 1 ? PPB : 1];
+    const int pl = threadIdx.x % PPB;
+    const int p = blockIdx.x * PPB + pl;
     const int cs = threadIdx.x / PPB;
-    if (p >= N) return;
-    const int b = p / HW, rem = p - b * HW;
-    const int n = min(ws.cnt[p], kSlots);
+    const bool live = p < N;
+    int n = 0;
     int src[kSlots];
     float w[kSlots];
-    const int4 *e4 = reinterpret_cast<const int4 *>(ws.ent + (size_t)p * kSlots);
+    if (cs == 0) {
+        n = live ? min(ws.cnt[p], kSlots) : 0;
+        const int4 *e4 = reinterpret_cast<const int4 *>(ws.ent + (size_t)p * kSlots);
 #pragma unroll
-    for (int i = 0; i < kSlots / 2; ++i) {
-        int4 e = make_int4(0, 0, 0, 0);
-        if (2 * i < n) e = e4[i];
-        src[2 * i] = (2 * i < n) ? e.x : 0x7fffffff;
-        w[2 * i] = (2 * i < n) ? __int_as_float(e.y) : 0.f;
-        src[2 * i + 1] = (2 * i + 1 < n) ? e.z : 0x7fffffff;
-        w[2 * i + 1] = (2 * i + 1 < n) ? __int_as_float(e.w) : 0.f;
-    }
-    // 19-comparator sorting network for 8 keys: list order no longer depends on atomic timing
+        for (int i = 0; i < kSlots / 2; ++i) {
+            int4 e = make_int4(0, 0, 0, 0);
+            if (2 * i < n) e = e4[i];
+            src[2 * i] = (2 * i < n) ? e.x : 0x7fffffff;
+            w[2 * i] = (2 * i < n) ? __int_as_float(e.y) : 0.f;
+            src[2 * i + 1] = (2 * i + 1 < n) ? e.z : 0x7fffffff;
+            w[2 * i + 1] = (2 * i + 1 < n) ? __int_as_float(e.w) : 0.f;
+        }
+        // 19-comparator sorting network for 8 keys: list order no longer depends on atomic timing
 #define USF_CS(a, b) cswap(src[a], w[a], src[b], w[b])
-    USF_CS(0, 1); USF_CS(2, 3); USF_CS(4, 5); USF_CS(6, 7);
-    USF_CS(0, 2); USF_CS(1, 3); USF_CS(4, 6); USF_CS(5, 7);
-    USF_CS(1, 2); USF_CS(5, 6); USF_CS(0, 4); USF_CS(3, 7);
-    USF_CS(1, 5); USF_CS(2, 6);
-    USF_CS(1, 4); USF_CS(3, 6);
-    USF_CS(2, 4); USF_CS(3, 5);
-    USF_CS(3, 4);
+        USF_CS(0, 1); USF_CS(2, 3); USF_CS(4, 5); USF_CS(6, 7);
+        USF_CS(0, 2); USF_CS(1, 3); USF_CS(4, 6); USF_CS(5, 7);
+        USF_CS(1, 2); USF_CS(5, 6); USF_CS(0, 4); USF_CS(3, 7);
+        USF_CS(1, 5); USF_CS(2, 6);
+        USF_CS(1, 4); USF_CS(3, 6);
+        USF_CS(2, 4); USF_CS(3, 5);
+        USF_CS(3, 4);
 #undef USF_CS
+        if (NS > 1) {
+#pragma unroll
+            for (int i = 0; i < kSlots; ++i) {
+                s_src[i][pl] = src[i];
+                s_w[i][pl] = w[i];
+            }
+            s_n[pl] = n;
+        }
+    }
+    if (NS > 1) {
+        __syncthreads();
+        if (cs != 0) {
+            n = s_n[pl];
+#pragma unroll
+            for (int i = 0; i < kSlots; ++i) {
+                src[i] = s_src[i][pl];
+                w[i] = s_w[i][pl];
+            }
+        }
+    }
+    if (!live) return;
+    const int b = p / HW, rem = p - b * HW;
     const size_t step = (size_t)NS * HW;
     const float *plane = gout + ((size_t)b * C + cs) * HW;
     float *o = gx + ((size_t)b * C + cs) * HW + rem;
     // most targets receive <= 4 taps (exactly 4 for a smooth flow): the upper half is a rarely taken branch
-#pragma unroll 2
+#pragma unroll 4
     for (int c = cs; c < C; c += NS, plane += step, o += step) {
         float acc = 0.f;
 #pragma unroll
@@ -386,7 +414,8 @@ int warp_bwd_f32(const float *x, const float *flow, const float *gout, float *gx
 #undef USF_LAUNCH
     st = note_launch(cudaGetLastError());
     if (st != USF_OK) return st;
-    warp_gx_overflow<<<148, kBlock, 0, stream>>>(gout, gx, ws, 4 * N, C, HW);
+    // fixed grid (the entry count lives on the device): 8 CTAs per SM, grid-stride over entries x channels
+    warp_gx_overflow<<<148 * 8, kBlock, 0, stream>>>(gout, gx, ws, 4 * N, C, HW);
     return note_launch(cudaGetLastError());
 }
 

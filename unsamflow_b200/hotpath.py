@@ -27,11 +27,12 @@ NUM_LOSS_SCALES = 4                        # w_ph_scales [1,1,1,1,0], configs/ki
 K = ops.NUM_DISPLACEMENTS
 
 
-def synthetic_flow(B, h, w, sigma, gen, fine_sigma=0.1, cell=8):
+def synthetic_flow(B, h, w, sigma, gen, fine_sigma=0.05, cell=24):
     """Seeded synthetic flow with the spatial statistics of a real one: optical flow is piecewise
     smooth (PWC-Lite itself produces each level by bilinear x2 upsampling of the coarser flow plus a
     small residual, models/pwclite.py:299-301,368-371).  Coarse N(0, sigma^2) vectors on a `cell`-pixel
-    lattice, bilinearly interpolated, plus N(0, fine_sigma^2) per-pixel residual.  (White-noise flow,
+    lattice, bilinearly interpolated (flow gradient ~ sigma*sqrt(2)/cell = 0.18 px/px for the defaults),
+    plus N(0, fine_sigma^2) per-pixel residual.  (White-noise flow,
     as used in the parity tests, scatters every warp's taps over ~20 cache sectors and measures the
     gather hardware, not the kernel.)"""
     import torch.nn.functional as F
@@ -197,6 +198,15 @@ class HotPathStep:
     def run(self, ops_subset=None):
         for op in (self.ops if ops_subset is None else ops_subset):
             op.fn()
+
+    def measure_launches(self):
+        """Run the step once eagerly and read the library's own launch counter (kernels only; the
+        cudaMemsetAsync of the warp-bwd tap counters is not a kernel).  Updates every op.launches."""
+        for op in self.ops:
+            ops.reset_launch_count()
+            op.fn()
+            op.launches = ops.launch_count()
+        return self.launches_per_step
 
     @property
     def launches_per_step(self):
