@@ -52,6 +52,10 @@ def parse():
     ap.add_argument("--cpu-reps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--op-table", default="", help="write the per-op timing table (JSON) here")
+    ap.add_argument("--train-steps", type=int, default=10,
+                    help="timed steps of the full PWC-Lite training step (0 = skip); reported as train_step")
+    ap.add_argument("--streams", type=int, default=2, choices=[1, 2],
+                    help="2: the two flow directions of the step run on two CUDA streams inside the graphs")
     return ap.parse_args()
 
 
@@ -213,9 +217,32 @@ def capture(fn):
 
 def per_launch_bytes(op):
     B, C, H, W = op.shape
-    if op.kind == "corr_bwd":  # each of the two launches reads gO + one feature map and writes one gradient
-        return (81 + 2 * C) * 4 * B * H * W
-    return op.bytes // max(1, op.launches)
+    if op.kind == "corr_bwd" and op.launches == 2:  # cp.async fallback: one launch per gradient, each reads
+        return (81 + 2 * C) * 4 * B * H * W         # gO + one feature map and writes one gradient
+    return op.bytes // max(1, op.launches)            # fused TMA launch: the op's algorithmic bytes
+
+
+def time_train_step(args, local, world, barrier):
+    """Full synthetic PWC-Lite training step (unsamflow_b200/train_step.py): forward with_bk, unflow loss,
+    backward, clip, Adam; DDP over NCCL when world > 1 (per-GPU batch fixed: weak scaling)."""
+    from unsamflow_b200.train_step import TrainStep
+    torch.backends.cudnn.benchmark = True  # train.py:19
+    ts = TrainStep(args.batch, args.height, args.width, f"cuda:{local}", seed=42, batch_directions=True,
+                   ddp=world > 1)
+    for _ in range(3):
+        ts.step()
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.train_steps):
+        loss = ts.step()
+    b.record()
+    barrier()
+    info = {"what": "PWC-Lite kitti_base training step (fwd with_bk + unflow loss + bwd + clip + Adam), synthetic "
+                    f"{args.height}x{args.width} pairs, B={args.batch} per GPU, eager PyTorch around the usf kernels",
+            "batch_directions": True, "loss": float(loss), "ddp": world > 1,
+            "params": ts.model.num_parameters()}
+    return a.elapsed_time(b), info
 
 
 def run_ours(args):
@@ -265,16 +292,27 @@ def run_ours(args):
             json.dump(table, f, indent=1)
 
     # ---- graphs: A (before the dominant op), eager dominant op, B (after) ----------------------------
+    # --streams 2 (default): the two flow directions run on two streams inside graphs A and B (the
+    # reference calls its two decoders back to back although they are independent, pwclite.py:430-432);
+    # the dominant op always runs alone between the two events, so its duration is a kernel time.
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
         step.run()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-    before, after = step.ops[:dom_i], step.ops[dom_i + 1:]
-    gA = capture(lambda: step.run(before)) if before else None
-    gB = capture(lambda: step.run(after)) if after else None
-    gFull = capture(step.run)
+    if args.streams == 2:
+        pre, post = step.split_around(dom)
+        step.run_concurrent(pre); dom.fn(); step.run_concurrent(post)  # warm the side stream up
+        torch.cuda.synchronize()
+        gA = capture(lambda: step.run_concurrent(pre))
+        gB = capture(lambda: step.run_concurrent(post))
+        gFull = capture(lambda: step.run_concurrent(step.chains))
+    else:
+        before, after = step.ops[:dom_i], step.ops[dom_i + 1:]
+        gA = capture(lambda: step.run(before)) if before else None
+        gB = capture(lambda: step.run(after)) if after else None
+        gFull = capture(step.run)
 
     def one_step(e0=None, e1=None):
         if gA is not None:
@@ -334,10 +372,16 @@ def run_ours(args):
     e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_marks)
     sampler.stop_flag = True
 
-    stats = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=step.device)
+    # ---- the whole PWC-Lite training step around the path (cuDNN convs + loss + Adam are PyTorch) --------
+    train_ms, train_info = 0.0, None
+    if args.train_steps > 0:
+        del gA, gB, gFull
+        train_ms, train_info = time_train_step(args, local, world, barrier)
+
+    stats = torch.tensor([total_ms, e2e_ms, train_ms], dtype=torch.float64, device=step.device)
     if dist is not None:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = stats.tolist()
+    total_ms, e2e_ms, train_ms = stats.tolist()
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -352,7 +396,8 @@ def run_ours(args):
             "config": workload_config(args, extra={
                 "l2": "256 MB L2 flush between timed steps (outside the per-step CUDA-event pair); "
                       "step working set ~1 GB > 126 MB L2",
-                "step": "CUDA graph A + eager dominant op between events + CUDA graph B"}),
+                "step": "CUDA graph A + eager dominant op between events + CUDA graph B",
+                "streams": args.streams}),
             "hot_path_gbs": world * step.bytes_per_step * args.steps / (total_ms / 1e3) / 1e9,
             "hot_path_tflops": world * step.flops_per_step * args.steps / (total_ms / 1e3) / 1e12,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -370,6 +415,10 @@ def run_ours(args):
                                  "through the C ABI in the timed region, the rest replayed from CUDA graphs)",
             "clocks": clocks,
         }
+        if train_info is not None:
+            train_info.update({"value": world * args.batch * args.train_steps / (train_ms / 1e3), "unit": UNIT,
+                               "ms_per_step": train_ms / args.train_steps, "steps": args.train_steps})
+            line["train_step"] = train_info
         if world == 1 and not args.no_cpu_baseline:
             cb = time_cpu_reference(args, steps=args.cpu_reps, warmup=1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

@@ -57,3 +57,60 @@ def test_per_rank_batch_follows_reference():
     with pytest.raises(ValueError):
         dist_util.per_rank_batch(4, 8)
     assert dist_util.max_over_ranks([1.5]) == [1.5]  # single process: identity
+
+
+def _ddp_worker(rank, world, port, q):
+    """DDP over gloo on CPU; the hot-path ops are swapped for the torch port in this TEST process only."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import unsamflow_b200.flow_loss as fl
+    import unsamflow_b200.pwclite as pw
+    from oracle import torch_port
+
+    class PortCorr(torch.nn.Module):
+        def __init__(self, *a, **k):
+            super().__init__()
+
+        def forward(self, a, b):
+            return torch_port.cost_volume(a, b)
+
+    pw.Correlation, pw.flow_warp, fl.flow_warp = PortCorr, torch_port.flow_warp, torch_port.flow_warp
+    from unsamflow_b200.train_step import TrainStep
+    torch.set_num_threads(2)
+    dist_util.init_from_env("gloo")
+    ts = TrainStep(1, 64, 128, "cpu", seed=7, ddp=True, lr=0.0)  # lr 0: weights stay put, grads stay readable
+    # local (non-DDP) gradient of this rank's own pair, same weights
+    out = ts.model(ts.img1, ts.img2, with_bk=True)
+    flows = [torch.cat([a, b], 1) for a, b in zip(out["flows_12"], out["flows_21"])]
+    ts.loss_fn(flows, ts.img1, ts.img2).backward()
+    probe = ts.model.flow_estimators.conv1[0].weight
+    local = probe.grad.detach().clone()
+    ts.model.zero_grad(set_to_none=True)
+    # one DDP step (clip_grad_norm_ rescales, so read the gradient through a hook-free second backward)
+    out = ts.net(ts.img1, ts.img2, with_bk=True)
+    flows = [torch.cat([a, b], 1) for a, b in zip(out["flows_12"], out["flows_21"])]
+    ts.loss_fn(flows, ts.img1, ts.img2).backward()
+    ddp_grad = probe.grad.detach().clone()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    mean_local = sum(gathered) / world
+    q.put((rank, float((ddp_grad - mean_local).abs().max()), float(mean_local.abs().max()),
+           bool(torch.equal(gathered[0], gathered[1]))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ddp_gradients_are_the_rank_average():
+    """train.py:116-120 semantics: batch sharded over ranks, DDP all-reduce averages the gradients."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    for rank, err, scale, same in out:
+        assert not same            # the ranks really saw different pairs
+        assert err <= 1e-5 * max(scale, 1e-12) + 1e-9, (rank, err, scale)

@@ -192,12 +192,46 @@ class HotPathStep:
                                      ops.warp_bwd(x, fl, gr, pad, need_gx=False, gflow=gfl)),
                                     warp_bwd_bytes(*shp, need_gx=False), shape=shp))
         # backward runs after the whole forward, finest level first (autograd order)
-        return fwd + bwd[::-1]
+        allops = fwd + bwd[::-1]
+        # per-direction chains (forward then backward of one decoder + its loss warps): the two
+        # directions share only read-only inputs, so they may run on two streams (run_concurrent)
+        self.chains = {d: [op for op in allops if op.name.endswith(d)] for d in ("d12", "d21")}
+        return allops
 
     # -- execution ------------------------------------------------------------------------------
     def run(self, ops_subset=None):
         for op in (self.ops if ops_subset is None else ops_subset):
             op.fn()
+
+    def run_concurrent(self, per_stream):
+        """Run {"d12": [ops], "d21": [ops]} on two streams forked from / joined to the current
+        stream (works under CUDA-graph capture).  PWCLite.forward calls its two decoders back to back
+        (models/pwclite.py:430-432) although they are independent; this is that overlap."""
+        main = torch.cuda.current_stream()
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        fork = torch.cuda.Event()
+        fork.record(main)
+        self._side.wait_event(fork)
+        with torch.cuda.stream(self._side):
+            for op in per_stream.get("d21", []):
+                op.fn()
+        for op in per_stream.get("d12", []):
+            op.fn()
+        join = torch.cuda.Event()
+        join.record(self._side)
+        main.wait_event(join)
+
+    def split_around(self, dom):
+        """(pre, post) stream dictionaries around one op: everything that must precede `dom` in its
+        own chain plus the other direction's forward goes to pre, the rest to post."""
+        d = "d12" if dom.name.endswith("d12") else "d21"
+        o = "d21" if d == "d12" else "d12"
+        chain = self.chains[d]
+        i = chain.index(dom)
+        other = self.chains[o]
+        nf = sum(1 for op in other if "fwd" in op.kind)
+        return ({d: chain[:i], o: other[:nf]}, {d: chain[i + 1:], o: other[nf:]})
 
     def measure_launches(self):
         """Run the step once eagerly and read the library's own launch counter (kernels only; the

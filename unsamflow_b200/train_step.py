@@ -1,0 +1,47 @@
+"""Synthetic-input PWC-Lite training step, single GPU or DDP (one process per GPU).
+
+Mirrors what the reference does per iteration at stage 0 (trainer/kitti_trainer_ar.py:99-131,309-317):
+model(img1, img2, with_bk=True) -> cat(flow12, flow21) per scale -> unFlowLoss -> zero_grad ->
+backward -> clip_grad_norm_(10) -> Adam step, and how it launches (train.py:42-147): NCCL process
+group, per-GPU batch = batch_size // world_size, DistributedDataParallel on the flow model only (the
+reference also wraps an unused MaskUNet, train.py:121-126 -- not replicated).
+The 10 MB gradient all-reduce is the only collective; DDP is configured for one bucket
+(bucket_cap_mb=16, gradient_as_bucket_view, static_graph) as SURVEY.md 5 recommends.
+"""
+import torch
+import torch.distributed as dist
+from torch.nn.parallel import DistributedDataParallel
+
+from .flow_loss import UnFlowLoss
+from .pwclite import PWCLite
+
+
+class TrainStep:
+    def __init__(self, batch, height, width, device, seed=42, batch_directions=False, ddp=False, lr=2e-4):
+        torch.manual_seed(seed)
+        self.device = torch.device(device)
+        self.model = PWCLite(batch_directions=batch_directions).to(self.device)
+        self.model.init_weights()
+        self.net = self.model
+        if ddp:
+            self.net = DistributedDataParallel(
+                self.model, device_ids=[self.device.index] if self.device.type == "cuda" else None,
+                bucket_cap_mb=16, gradient_as_bucket_view=True, static_graph=True)
+        self.loss_fn = UnFlowLoss()
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-7)
+        gen = torch.Generator().manual_seed(seed + (dist.get_rank() if ddp else 0))
+        self.img1 = torch.rand(batch, 3, height, width, generator=gen).to(self.device)
+        self.img2 = torch.rand(batch, 3, height, width, generator=gen).to(self.device)
+        self.batch = batch
+
+    def step(self, img1=None, img2=None):
+        img1 = self.img1 if img1 is None else img1
+        img2 = self.img2 if img2 is None else img2
+        out = self.net(img1, img2, with_bk=True)
+        flows = [torch.cat([f12, f21], 1) for f12, f21 in zip(out["flows_12"], out["flows_21"])]
+        loss = self.loss_fn(flows, img1, img2)
+        self.opt.zero_grad(set_to_none=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(self.model.parameters(), 10.0)
+        self.opt.step()
+        return loss.detach()
