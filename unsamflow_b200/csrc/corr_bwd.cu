@@ -310,8 +310,6 @@ __device__ __forceinline__ void bwd_tile(unsigned char *smem_raw, const CUtensor
         mbar_wait(&gfull[s], (dyi >> 1) & 1);
         float g[kD][8];
         GLoader<GX2, 0>::run(g, reinterpret_cast<const float *>(gbase + s * GB), r, q);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&gempty[s]);  // G values now live in registers
 #pragma unroll
         for (int c = 0; c < CT; ++c) {
             const float *p = xw + (c * XR + dyi) * XS;
@@ -322,6 +320,14 @@ __device__ __forceinline__ void bwd_tile(unsigned char *smem_raw, const CUtensor
             for (int dx = 0; dx < kD; ++dx)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(g[dx][i], w[dx + i], acc[c][i]);
+            if (c == 0) {
+                // Release the G stage only after the first channel's FFMAs have CONSUMED every g value:
+                // an arrive issued right after the LDS instructions does not wait for their data, and the
+                // producer's next TMA write then races with loads still in flight (seen as rare, large
+                // errors in gx2 at 8x32x64x208).
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&gempty[s]);
+            }
         }
     }
 
