@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--op-table", default="", help="write the per-op timing table (JSON) here")
     ap.add_argument("--train-steps", type=int, default=10,
                     help="timed steps of the full PWC-Lite training step (0 = skip); reported as train_step")
+    ap.add_argument("--batch-directions", action="store_true",
+                    help="evaluate the two flow directions as one batch of 2B pairs (half the launches)")
     ap.add_argument("--streams", type=int, default=2, choices=[1, 2],
                     help="2: the two flow directions of the step run on two CUDA streams inside the graphs")
     return ap.parse_args()
@@ -264,7 +266,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    step = HotPathStep(args.batch, args.height, args.width, device=f"cuda:{local}", flow_sigma=args.flow_sigma)
+    step = HotPathStep(args.batch, args.height, args.width, device=f"cuda:{local}", flow_sigma=args.flow_sigma,
+                       batch_directions=args.batch_directions)
+    if args.batch_directions:
+        args.streams = 1
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=step.device)  # > 126 MB L2
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
@@ -397,7 +402,7 @@ def run_ours(args):
                 "l2": "256 MB L2 flush between timed steps (outside the per-step CUDA-event pair); "
                       "step working set ~1 GB > 126 MB L2",
                 "step": "CUDA graph A + eager dominant op between events + CUDA graph B",
-                "streams": args.streams}),
+                "streams": args.streams, "batch_directions": args.batch_directions}),
             "hot_path_gbs": world * step.bytes_per_step * args.steps / (total_ms / 1e3) / 1e9,
             "hot_path_tflops": world * step.flops_per_step * args.steps / (total_ms / 1e3) / 1e12,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -99,7 +99,15 @@ class OpRecord:
 class HotPathStep:
     """Preallocated synthetic inputs/outputs + the ordered op list of one training step."""
 
-    def __init__(self, B, H, W, device="cuda", seed=42, flow_sigma=3.0, pad="border", flow_kind="smooth"):
+    def __init__(self, B, H, W, device="cuda", seed=42, flow_sigma=3.0, pad="border", flow_kind="smooth",
+                 batch_directions=False):
+        """batch_directions: evaluate flows_12 and flows_21 as ONE batch of 2B pairs (x1 = [f1;f2],
+        x2 = [f2;f1]) like PWCLite(batch_directions=True): same math, half the launches."""
+        self.pairs = B
+        self.batch_directions = batch_directions
+        self.dirs = ("d12",) if batch_directions else ("d12", "d21")
+        if batch_directions:
+            B = 2 * B
         self.B, self.H, self.W, self.pad = B, H, W, pad
         self.flow_kind = flow_kind
         self.device = torch.device(device)
@@ -121,7 +129,7 @@ class HotPathStep:
             for n in ("f1", "f2"):
                 t[f"{n}.L{lvl}"] = randn(B, C, h, w)
                 self.input_names.append(f"{n}.L{lvl}")
-            for d in ("d12", "d21"):
+            for d in self.dirs:
                 if lvl > 0:
                     t[f"flow.L{lvl}.{d}"] = flow(h, w)
                     t[f"x2w.L{lvl}.{d}"] = torch.empty(B, C, h, w, device=self.device)
@@ -139,7 +147,7 @@ class HotPathStep:
             for n in ("im1", "im2"):
                 t[f"{n}.S{s}"] = torch.rand(B, C, h, w, generator=gen).to(self.device)
                 self.input_names.append(f"{n}.S{s}")
-            for d in ("d12", "d21"):
+            for d in self.dirs:
                 t[f"lflow.S{s}.{d}"] = flow(h, w)
                 t[f"recons.S{s}.{d}"] = torch.empty(B, C, h, w, device=self.device)
                 t[f"grecons.S{s}.{d}"] = randn(B, C, h, w)
@@ -151,7 +159,7 @@ class HotPathStep:
     def _build_ops(self):
         t, B, pad = self.t, self.B, self.pad
         fwd, bwd = [], []
-        for d in ("d12", "d21"):
+        for d in self.dirs:
             a, b = ("f1", "f2") if d == "d12" else ("f2", "f1")
             for lvl, (C, h, w) in enumerate(self.levels):
                 x1, x2 = t[f"{a}.L{lvl}"], t[f"{b}.L{lvl}"]
@@ -195,7 +203,7 @@ class HotPathStep:
         allops = fwd + bwd[::-1]
         # per-direction chains (forward then backward of one decoder + its loss warps): the two
         # directions share only read-only inputs, so they may run on two streams (run_concurrent)
-        self.chains = {d: [op for op in allops if op.name.endswith(d)] for d in ("d12", "d21")}
+        self.chains = {d: [op for op in allops if op.name.endswith(d)] for d in self.dirs}
         return allops
 
     # -- execution ------------------------------------------------------------------------------
@@ -260,4 +268,4 @@ class HotPathStep:
     def result_names(self):
         """What a caller reads back: gradients at the finest model level and loss scale."""
         top = len(self.levels) - 1
-        return [f"gx1.L{top}.d12", f"gflow.L{top}.d12", "glflow.S0.d12", "glflow.S0.d21"]
+        return [f"gx1.L{top}.d12", f"gflow.L{top}.d12"] + [f"glflow.S0.{d}" for d in self.dirs]
