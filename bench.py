@@ -217,6 +217,16 @@ def capture(fn):
     return g
 
 
+def ncu_traffic(op):
+    """DRAM bytes per launch of this op's kernel from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get(f"{op.kind}." + "x".join(str(v) for v in op.shape))
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def per_launch_bytes(op):
     B, C, H, W = op.shape
     if op.kind == "corr_bwd" and op.launches == 2:  # cp.async fallback: one launch per gradient, each reads
@@ -406,7 +416,7 @@ def run_ours(args):
             "hot_path_gbs": world * step.bytes_per_step * args.steps / (total_ms / 1e3) / 1e9,
             "hot_path_tflops": world * step.flops_per_step * args.steps / (total_ms / 1e3) / 1e12,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": dom.name, "kind": dom.kind, "shape": list(dom.shape),
+                         "traffic": ncu_traffic(dom), "kernel": dom.name, "kind": dom.kind, "shape": list(dom.shape),
                          "launches_per_op": launches, "alg_bytes_per_launch": alg, "us_per_launch": dom_us,
                          "peak_source": peak_src,
                          "fp32_tflops": (dom.flops / launches) / dom_us / 1e6 if dom.flops else None,
