@@ -64,6 +64,8 @@ def main():
     ap.add_argument("--sigma", type=float, default=3.0)
     ap.add_argument("--out", default="")
     ap.add_argument("--flow", default="smooth", choices=["smooth", "iid"])
+    ap.add_argument("--preset", default="", choices=["", "sweep"],
+                    help="sweep: BASELINE.json configs[4] (C=32..196, every pyramid level, B=1..64)")
     args = ap.parse_args()
     global FLOW_KIND
     FLOW_KIND = args.flow
@@ -81,9 +83,17 @@ def main():
     except Exception:  # noqa: BLE001
         pynvml, nvh = None, None
     inner = 1 if args.cold else args.inner
+    work = [(op, s) for op in args.ops.split(",") for s in args.shapes.split(",")]
+    if args.preset == "sweep":
+        lv = [(192, 4, 13), (128, 8, 26), (96, 16, 52), (64, 32, 104), (32, 64, 208)]
+        shapes = [f"{b}x{c}x{h}x{w}" for (c, h, w) in lv for b in (1, 8, 64)]
+        shapes += [f"8x{c}x64x208" for c in (64, 96, 128, 192, 196)]                 # channel sweep at the largest level
+        shapes += ["4x32x96x208", "4x64x48x104", "4x32x112x256", "8x32x48x160", "8x32x80x176"]  # Sintel / crops
+        work = [(op, s) for op in ("corr_fwd", "corr_bwd", "warp_fwd", "warp_bwd") for s in shapes]
+        work += [(op, s) for op in ("warp_fwd", "warp_bwd_flow") for s in ("8x3x256x832", "4x3x384x832", "4x3x448x1024")]
     rows = []
-    for op in args.ops.split(","):
-        for s in args.shapes.split(","):
+    for op, s in work:
+        if True:
             shape = tuple(int(v) for v in s.split("x"))
             fn, nbytes, flops, launches = build(op, shape, args.sigma)
             for _ in range(3):

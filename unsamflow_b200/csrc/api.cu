@@ -2,6 +2,10 @@
 // Validates arguments, dispatches on dtype, never allocates, never synchronises.
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace usf {
@@ -23,6 +27,24 @@ static thread_local int tl_cuda_error = 0;
 static thread_local unsigned long long tl_launches = 0;
 
 void note_cuda_error(cudaError_t e) { tl_cuda_error = (int)e; }
+
+cudaError_t ensure_smem(const void *kernel, int smem_bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, int> done;  // (kernel, device) -> bytes already granted
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(kernel, dev);
+    auto it = done.find(key);
+    if (it != done.end() && it->second >= smem_bytes) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    done[key] = smem_bytes;
+    return cudaSuccess;
+}
 
 int note_launch(cudaError_t e) {
     if (e != cudaSuccess) {
@@ -119,6 +141,7 @@ int usf_warp_bwd(const void *x, const float *flow, const void *gout, void *gx, f
     if (int st = check_dims(B, C, H, W, 2)) return st;
     if (H < 2 || W < 2) return USF_ERR_BAD_SHAPE;
     if (!gx && !gflow) return USF_OK;
+    if (gx && (long long)B * H * W > (1LL << 29)) return USF_ERR_BAD_SHAPE;  // 4*N tap bound stays in int
     if (dtype == USF_F32)
         return warp_bwd_f32((const float *)x, flow, (const float *)gout, (float *)gx, gflow, B, C, H, W,
                             pad_mode, flags, workspace, workspace_bytes, (cudaStream_t)stream);

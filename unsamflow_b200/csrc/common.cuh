@@ -17,6 +17,9 @@ extern long kDirectMaxPixels;
 // ---- host-side bookkeeping (api.cu) ---------------------------------------
 int note_launch(cudaError_t e);        // counts a launch, records e; returns usf_status
 void note_cuda_error(cudaError_t e);
+// Opt a kernel into `smem_bytes` of dynamic shared memory (+ max shared carve-out) once per (kernel, device).
+// cudaFuncSetAttribute is per device, so a process that drives several GPUs is handled too.
+cudaError_t ensure_smem(const void *kernel, int smem_bytes);
 
 // ---- cp.async (LDGSTS) ------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

@@ -370,13 +370,7 @@ cudaError_t launch_tma(const CUtensorMap &mx1, const CUtensorMap &mg1, const CUt
                        const CUtensorMap &mg2, float *gx1, float *gx2, int B, int C, int H, int W,
                        cudaStream_t stream) {
     constexpr int SM = GTile<true>::kSmem > GTile<false>::kSmem ? GTile<true>::kSmem : GTile<false>::kSmem;
-    static cudaError_t once = [] {
-        cudaError_t e = cudaFuncSetAttribute(corr_bwd_gather_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, SM);
-        if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(corr_bwd_gather_tma, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    cudaSharedmemCarveoutMaxShared);
-    }();
-    if (once != cudaSuccess) return once;
+    if (cudaError_t once = ensure_smem((const void *)corr_bwd_gather_tma, SM)) return once;
     const int ngroups = (C + CG - 1) / CG;
     const int nz = B * ngroups;
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, nz * ((gx1 && gx2) ? 2 : 1));
@@ -388,9 +382,7 @@ cudaError_t launch_tma(const CUtensorMap &mx1, const CUtensorMap &mg1, const CUt
 template <bool GX2, bool VEC>
 cudaError_t launch(const float *xin, const float *gout, float *gx, int B, int C, int H, int W,
                    cudaStream_t stream) {
-    static cudaError_t once = cudaFuncSetAttribute(corr_bwd_gather<GX2, VEC>,
-                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    (void)once;
+    if (cudaError_t once = ensure_smem((const void *)corr_bwd_gather<GX2, VEC>, SMEM_BYTES)) return once;
     const int ngroups = (C + CG - 1) / CG;
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, B * ngroups);
     corr_bwd_gather<GX2, VEC><<<grid, NTHREADS, SMEM_BYTES, stream>>>(xin, gout, gx, C, H, W, ngroups,
@@ -405,13 +397,14 @@ int corr_bwd_direct_f32(const float *, const float *, const float *, float *, fl
 
 int corr_bwd_f32(const float *x1, const float *x2, const float *gout, float *gx1, float *gx2, int B, int C,
                  int H, int W, cudaStream_t stream) {
-    if ((long)B * H * W <= kDirectMaxPixels) return corr_bwd_direct_f32(x1, x2, gout, gx1, gx2, B, C, H, W, stream);
+    // (widths TMA can address go to the tiled kernels even when small)
+    if ((long)B * H * W <= kDirectMaxPixels && (W % 4) != 0) return corr_bwd_direct_f32(x1, x2, gout, gx1, gx2, B, C, H, W, stream);
     const bool vec = (W % 4 == 0) &&
                      (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)gout | (uintptr_t)gx1 | (uintptr_t)gx2) % 16 == 0);
     int st = USF_OK;
     if (vec) {
         // TMA path (tensor maps encoded per call, passed as __grid_constant__ parameters)
-        CUtensorMap mx1, mg1, mx2, mg2;
+        CUtensorMap mx1 = {}, mg1 = {}, mx2 = {}, mg2 = {};
         bool ok = true;
         if (gx1) ok = make_nchw_map(&mx1, x2, B, C, H, W, XS, XR, CT) && make_nchw_map(&mg1, gout, B, kK, H, W, GS, TH, kD);
         if (ok && gx2) ok = make_nchw_map(&mx2, x1, B, C, H, W, XS, XR, CT) && make_nchw_map(&mg2, gout, B, kK, H, W, XS, TH, kD);

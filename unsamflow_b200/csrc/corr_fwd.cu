@@ -484,31 +484,24 @@ corr_fwd_splitc_tma(const __grid_constant__ CUtensorMap m1, const __grid_constan
     }
 }
 
-template <typename K>
-cudaError_t prep(K kernel, int smem_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-}
-
 template <bool LEAKY>
 cudaError_t launch_tma(bool splitc, const CUtensorMap &m1, const CUtensorMap &m2a, const CUtensorMap &m2b,
                        float *out, int B, int C, int H, int W, int tx, int ty, float rc, float slope,
                        cudaStream_t stream) {
     if (splitc) {
-        static cudaError_t once = prep(corr_fwd_splitc_tma<LEAKY>, TB_SMEM);
+        cudaError_t once = ensure_smem((const void *)corr_fwd_splitc_tma<LEAKY>, TB_SMEM);
         if (once != cudaSuccess) return once;
         corr_fwd_splitc_tma<LEAKY><<<dim3(tx, ty, B * kD), TB_THREADS, TB_SMEM, stream>>>(m1, m2b, out, C, H, W, rc, slope);
     } else {
         const int ntiles = tx * ty * B;
         if (ntiles * 2 <= 3 * 148) {  // at most 1.5 tiles per SM: one pipelined CTA per SM
-            static cudaError_t once = prep(corr_fwd_tile9_tma<LEAKY, true>, T9Cfg<true>::kSmem);
+            cudaError_t once = ensure_smem((const void *)corr_fwd_tile9_tma<LEAKY, true>, T9Cfg<true>::kSmem);
             if (once != cudaSuccess) return once;
             const int grid = ntiles < 148 ? ntiles : 148;
             corr_fwd_tile9_tma<LEAKY, true><<<grid, TA_THREADS, T9Cfg<true>::kSmem, stream>>>(
                 m1, m2a, out, C, H, W, tx, ty, ntiles, rc, slope);
         } else {
-            static cudaError_t once = prep(corr_fwd_tile9_tma<LEAKY, false>, T9Cfg<false>::kSmem);
+            cudaError_t once = ensure_smem((const void *)corr_fwd_tile9_tma<LEAKY, false>, T9Cfg<false>::kSmem);
             if (once != cudaSuccess) return once;
             const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;
             corr_fwd_tile9_tma<LEAKY, false><<<grid, TA_THREADS, T9Cfg<false>::kSmem, stream>>>(
@@ -518,11 +511,6 @@ cudaError_t launch_tma(bool splitc, const CUtensorMap &m1, const CUtensorMap &m2
     return cudaGetLastError();
 }
 
-template <typename K>
-cudaError_t set_smem(K kernel, int bytes) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-}
-
 }  // namespace
 
 int corr_fwd_direct_f32(const float *, const float *, float *, int, int, int, int, unsigned, float, cudaStream_t);
@@ -530,7 +518,8 @@ int corr_fwd_direct_f32(const float *, const float *, float *, int, int, int, in
 int corr_fwd_f32(const float *x1, const float *x2, float *out, int B, int C, int H, int W, unsigned flags,
                  float slope, cudaStream_t stream) {
     // tiny levels (KITTI 4x13, 8x26): latency-bound, L1/L2 resident -> direct kernel (corr_direct.cu)
-    if ((long)B * H * W <= kDirectMaxPixels) return corr_fwd_direct_f32(x1, x2, out, B, C, H, W, flags, slope, stream);
+    // (widths TMA can address go to the tiled kernels even when small)
+    if ((long)B * H * W <= kDirectMaxPixels && (W % 4) != 0) return corr_fwd_direct_f32(x1, x2, out, B, C, H, W, flags, slope, stream);
     const bool vec = (W % 4 == 0) && (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) % 16 == 0);
     const int tx = (W + TW - 1) / TW, ty = (H + TH - 1) / TH;
     const float rc = 1.0f / (float)C;
@@ -554,23 +543,19 @@ int corr_fwd_f32(const float *x1, const float *x2, float *out, int B, int C, int
     if (splitc) {
         dim3 grid(tx, ty, B * kD);
         if (vec) {
-            static cudaError_t once = set_smem(corr_fwd_splitc<true>, B_SMEM);
-            (void)once;
+            if (cudaError_t once = ensure_smem((const void *)corr_fwd_splitc<true>, B_SMEM)) return note_launch(once);
             corr_fwd_splitc<true><<<grid, B_THREADS, B_SMEM, stream>>>(x1, x2, out, C, H, W, rc, leaky, slope);
         } else {
-            static cudaError_t once = set_smem(corr_fwd_splitc<false>, B_SMEM);
-            (void)once;
+            if (cudaError_t once = ensure_smem((const void *)corr_fwd_splitc<false>, B_SMEM)) return note_launch(once);
             corr_fwd_splitc<false><<<grid, B_THREADS, B_SMEM, stream>>>(x1, x2, out, C, H, W, rc, leaky, slope);
         }
     } else {
         dim3 grid(tx, ty, B);
         if (vec) {
-            static cudaError_t once = set_smem(corr_fwd_tile9<true>, A_SMEM);
-            (void)once;
+            if (cudaError_t once = ensure_smem((const void *)corr_fwd_tile9<true>, A_SMEM)) return note_launch(once);
             corr_fwd_tile9<true><<<grid, A_THREADS, A_SMEM, stream>>>(x1, x2, out, C, H, W, rc, leaky, slope);
         } else {
-            static cudaError_t once = set_smem(corr_fwd_tile9<false>, A_SMEM);
-            (void)once;
+            if (cudaError_t once = ensure_smem((const void *)corr_fwd_tile9<false>, A_SMEM)) return note_launch(once);
             corr_fwd_tile9<false><<<grid, A_THREADS, A_SMEM, stream>>>(x1, x2, out, C, H, W, rc, leaky, slope);
         }
     }
