@@ -49,9 +49,10 @@ typedef enum usf_status {
     USF_ERR_BAD_ARG = -2,     /* null pointer, unknown dtype / pad mode / flag, md != 4 */
     USF_ERR_WORKSPACE = -3,   /* workspace missing or smaller than usf_warp_bwd_workspace_bytes */
     USF_ERR_CUDA = -4,        /* a CUDA runtime call failed; see usf_last_cuda_error() */
-    USF_ERR_UNSUPPORTED = -5  /* valid request this build does not implement */
+    USF_ERR_UNSUPPORTED = -5  /* valid request this build does not implement (none at ABI version 1) */
 } usf_status;
 
+/* storage type of feature tensors; arithmetic is fp32 either way (bf16: one rounding per output element) */
 typedef enum usf_dtype { USF_F32 = 0, USF_BF16 = 1 } usf_dtype;
 
 /* padding_mode of flow_warp (utils/warp_utils.py:97: pad="border" | "zeros") */

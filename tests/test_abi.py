@@ -49,7 +49,6 @@ def test_argument_validation_without_a_gpu(lib):
     assert lib.usf_corr_fwd(p, p, p, 1, 1, 2, 2, 3, 0, 0, 0.0, None) == BAD_ARG
     assert lib.usf_corr_fwd(p, p, p, 1, 1, 2, 2, 4, 0, 64, 0.0, None) == BAD_ARG
     assert lib.usf_corr_fwd(p, p, p, 1, 1, 2, 2, 4, 7, 0, 0.0, None) == BAD_ARG
-    assert lib.usf_corr_fwd(p, p, p, 1, 1, 2, 2, 4, 1, 0, 0.0, None) == UNSUPPORTED  # bf16: not yet
     # shapes: non-positive, and more than 2^31-1 elements
     assert lib.usf_corr_fwd(p, p, p, 0, 1, 2, 2, 4, 0, 0, 0.0, None) == BAD_SHAPE
     assert lib.usf_corr_fwd(p, p, p, 64, 512, 1024, 1024, 4, 0, 0, 0.0, None) == BAD_SHAPE

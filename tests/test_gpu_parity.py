@@ -368,7 +368,9 @@ def test_errors_are_loud(usf):
     with pytest.raises(NotImplementedError):
         usf.flow_warp(x, torch.zeros(1, 2, 8, 8).cuda(), mode="nearest")
     with pytest.raises(NotImplementedError):
-        ops.corr_fwd(x.half(), x.half())
+        ops.corr_fwd(x.half(), x.half())          # fp16 is not a supported storage type
+    with pytest.raises(ValueError):
+        ops.corr_fwd(x, x.bfloat16())
 
 
 def test_cuda_graph_capture_of_a_step(usf):
@@ -424,3 +426,75 @@ def test_corr_kernels_are_bit_deterministic_under_load(usf):
         a, b = ops.corr_bwd(x1, x2, go)
         assert torch.equal(a, a0) and torch.equal(b, b0)
         assert torch.equal(ops.corr_fwd(x1, x2), o0)
+
+
+# --------------------------------------------------------------------------------------------
+# bf16 storage (new capability): fp32 accumulate, fp32 flow / coordinates.
+# Stated tolerance: rel-L2 <= 4e-3 and max-norm <= 8e-3 against the fp32 oracle evaluated on the
+# SAME bf16-rounded inputs (i.e. one bf16 rounding of each output, 2^-9 relative).
+# --------------------------------------------------------------------------------------------
+BF16_L2, BF16_MAX = 4e-3, 8e-3
+
+
+def check_bf16(got, want, what):
+    got = got.detach().float().cpu().numpy()
+    assert np.isfinite(got).all(), what
+    e1, e2 = rel_l2(got, want), max_norm_err(got, want)
+    assert e1 <= BF16_L2 and e2 <= BF16_MAX, f"{what}: rel_l2={e1:.3e} max_norm={e2:.3e}"
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 8, 26), (1, 33, 5, 11), (2, 32, 32, 104), (1, 96, 16, 52)],
+                         ids=lambda s: "x".join(map(str, s)))
+def test_bf16_corr_vs_oracle(usf, shape):
+    from oracle import c_oracle
+    ops = usf.ops_mod
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(C + W)
+    x1 = torch.randn(shape, generator=g).bfloat16()
+    x2 = torch.randn(shape, generator=g).bfloat16()
+    go = torch.randn(B, 81, H, W, generator=g).bfloat16()
+    out = ops.corr_fwd(x1.cuda(), x2.cuda())
+    assert out.dtype == torch.bfloat16
+    check_bf16(out, c_oracle.corr_fwd(x1.float().numpy(), x2.float().numpy()), "out")
+    g1, g2 = ops.corr_bwd(x1.cuda(), x2.cuda(), go.cuda())
+    o1, o2 = c_oracle.corr_bwd(x1.float().numpy(), x2.float().numpy(), go.float().numpy())
+    check_bf16(g1, o1, "gx1")
+    check_bf16(g2, o2, "gx2")
+
+
+@pytest.mark.parametrize("pad", ["border", "zeros"])
+@pytest.mark.parametrize("shape", [(2, 32, 16, 52), (1, 3, 64, 208), (1, 17, 9, 31)], ids=lambda s: "x".join(map(str, s)))
+def test_bf16_warp_vs_oracle(usf, shape, pad):
+    from oracle import c_oracle
+    ops = usf.ops_mod
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(C + H)
+    x = torch.randn(shape, generator=g).bfloat16()
+    go = torch.randn(shape, generator=g).bfloat16()
+    fl = 2.0 * torch.randn(B, 2, H, W, generator=g)
+    xn, gn, fn = x.float().numpy(), go.float().numpy(), fl.numpy()
+    out = ops.warp_fwd(x.cuda(), fl.cuda(), pad)
+    assert out.dtype == torch.bfloat16
+    check_bf16(out, c_oracle.warp_fwd(xn, fn, pad), "out")
+    gx, gf = ops.warp_bwd(x.cuda(), fl.cuda(), go.cuda(), pad)
+    ogx, ogf = c_oracle.warp_bwd(xn, fn, gn, pad)
+    assert gx.dtype == torch.bfloat16 and gf.dtype == torch.float32
+    check_bf16(gx, ogx, "gx")
+    check(gf, ogf, "gflow (fp32 accumulate over bf16 storage)")
+
+
+def test_bf16_autograd_decoder_level(usf):
+    """warp -> corr in bf16 through the public modules (autocast-style caller)."""
+    from oracle import c_oracle
+    g = torch.Generator().manual_seed(5)
+    x1 = torch.randn(1, 32, 16, 52, generator=g).bfloat16()
+    x2 = torch.randn(1, 32, 16, 52, generator=g).bfloat16()
+    fl = 1.5 * torch.randn(1, 2, 16, 52, generator=g)
+    a, b, f = x1.cuda().requires_grad_(True), x2.cuda().requires_grad_(True), fl.cuda().requires_grad_(True)
+    out = usf.Correlation()(a, usf.flow_warp(b, f))
+    out.float().sum().backward()
+    x2w = c_oracle.warp_fwd(x2.float().numpy(), fl.numpy(), "border")
+    x2w_b = torch.from_numpy(x2w).bfloat16().float().numpy()      # the warp output is stored in bf16
+    check_bf16(out, c_oracle.corr_fwd(x1.float().numpy(), x2w_b), "out")
+    assert a.grad.dtype == torch.bfloat16 and f.grad.dtype == torch.float32
+    assert torch.isfinite(a.grad.float()).all() and torch.isfinite(f.grad).all()

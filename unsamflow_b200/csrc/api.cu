@@ -17,6 +17,11 @@ int warp_fwd_f32(const float *, const float *, float *, int, int, int, int, int,
 int warp_bwd_f32(const float *, const float *, const float *, float *, float *, int, int, int, int, int,
                  unsigned, void *, size_t, cudaStream_t);
 size_t warp_bwd_workspace_bytes(size_t N);
+int corr_fwd_bf16(const void *, const void *, void *, int, int, int, int, unsigned, float, cudaStream_t);
+int corr_bwd_bf16(const void *, const void *, const void *, void *, void *, int, int, int, int, cudaStream_t);
+int warp_fwd_bf16(const void *, const float *, void *, int, int, int, int, int, unsigned, cudaStream_t);
+int warp_bwd_bf16(const void *, const float *, const void *, void *, float *, int, int, int, int, int, unsigned,
+                  void *, size_t, cudaStream_t);
 
 long kDirectMaxPixels = [] {
     const char *e = getenv("USF_DIRECT_MAX_PIXELS");
@@ -96,7 +101,7 @@ int usf_corr_fwd(const void *x1, const void *x2, void *out, int B, int C, int H,
     if (dtype == USF_F32)
         return corr_fwd_f32((const float *)x1, (const float *)x2, (float *)out, B, C, H, W, flags, leaky_slope,
                             (cudaStream_t)stream);
-    if (dtype == USF_BF16) return USF_ERR_UNSUPPORTED;
+    if (dtype == USF_BF16) return corr_fwd_bf16(x1, x2, out, B, C, H, W, flags, leaky_slope, (cudaStream_t)stream);
     return USF_ERR_BAD_ARG;
 }
 
@@ -108,7 +113,7 @@ int usf_corr_bwd(const void *x1, const void *x2, const void *gout, void *gx1, vo
     if (dtype == USF_F32)
         return corr_bwd_f32((const float *)x1, (const float *)x2, (const float *)gout, (float *)gx1,
                             (float *)gx2, B, C, H, W, (cudaStream_t)stream);
-    if (dtype == USF_BF16) return USF_ERR_UNSUPPORTED;
+    if (dtype == USF_BF16) return corr_bwd_bf16(x1, x2, gout, gx1, gx2, B, C, H, W, (cudaStream_t)stream);
     return USF_ERR_BAD_ARG;
 }
 
@@ -122,7 +127,7 @@ int usf_warp_fwd(const void *x, const float *flow, void *out, int B, int C, int 
     if (dtype == USF_F32)
         return warp_fwd_f32((const float *)x, flow, (float *)out, B, C, H, W, pad_mode, flags,
                             (cudaStream_t)stream);
-    if (dtype == USF_BF16) return USF_ERR_UNSUPPORTED;
+    if (dtype == USF_BF16) return warp_fwd_bf16(x, flow, out, B, C, H, W, pad_mode, flags, (cudaStream_t)stream);
     return USF_ERR_BAD_ARG;
 }
 
@@ -145,7 +150,9 @@ int usf_warp_bwd(const void *x, const float *flow, const void *gout, void *gx, f
     if (dtype == USF_F32)
         return warp_bwd_f32((const float *)x, flow, (const float *)gout, (float *)gx, gflow, B, C, H, W,
                             pad_mode, flags, workspace, workspace_bytes, (cudaStream_t)stream);
-    if (dtype == USF_BF16) return USF_ERR_UNSUPPORTED;
+    if (dtype == USF_BF16)
+        return warp_bwd_bf16(x, flow, gout, gx, gflow, B, C, H, W, pad_mode, flags, workspace, workspace_bytes,
+                             (cudaStream_t)stream);
     return USF_ERR_BAD_ARG;
 }
 

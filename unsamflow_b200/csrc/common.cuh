@@ -1,5 +1,6 @@
 // common.cuh -- shared device helpers for the corr / warp kernels (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -42,6 +43,15 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
+
+// storage-type agnostic scalar access: feature tensors are fp32 or bf16, arithmetic is always fp32
+typedef __nv_bfloat16 bf16;
+__device__ __forceinline__ float ldf(const float *p) { return __ldg(p); }
+__device__ __forceinline__ float ldf(const bf16 *p) { return __bfloat162float(__ldg(p)); }
+__device__ __forceinline__ void stf(float *p, float v) { *p = v; }
+__device__ __forceinline__ void stf(bf16 *p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void atomic_addf(float *p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void atomic_addf(bf16 *p, float v) { atomicAdd(p, __float2bfloat16_rn(v)); }
 
 __device__ __forceinline__ float4 lds128(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 

@@ -81,9 +81,9 @@ __device__ __forceinline__ float ldp(const float *__restrict__ base, int off, bo
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int NS>
+template <int NS, typename T>
 __global__ void __launch_bounds__(kBlock)
-warp_fwd_kernel(const float *__restrict__ x, const float *__restrict__ flow, float *__restrict__ out, int N,
+warp_fwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, T *__restrict__ out, int N,
                 int C, int H, int W, int border, int rcp) {
     constexpr int PPB = kBlock / NS;
     const int p = blockIdx.x * PPB + (threadIdx.x % PPB);
@@ -99,16 +99,16 @@ warp_fwd_kernel(const float *__restrict__ x, const float *__restrict__ flow, flo
     // two row pointers (taps nw/ne and sw/se are neighbours) bumped by one slice stride per channel:
     // no per-tap address arithmetic in the loop; out-of-image taps are predicated off, never read
     const size_t step = (size_t)NS * HW;
-    const float *p0 = x + ((size_t)b * C + cs) * HW + t.o_nw;
-    const float *p1 = p0 + W;
-    float *o = out + ((size_t)b * C + cs) * HW + rem;
+    const T *p0 = x + ((size_t)b * C + cs) * HW + t.o_nw;
+    const T *p1 = p0 + W;
+    T *o = out + ((size_t)b * C + cs) * HW + rem;
 #pragma unroll 4
     for (int c = cs; c < C; c += NS, p0 += step, p1 += step, o += step) {
-        float acc = (t.k_nw ? __ldg(p0) : 0.f) * nw;
-        acc = fmaf(t.k_ne ? __ldg(p0 + 1) : 0.f, ne, acc);
-        acc = fmaf(t.k_sw ? __ldg(p1) : 0.f, sw, acc);
-        acc = fmaf(t.k_se ? __ldg(p1 + 1) : 0.f, se, acc);
-        *o = acc;
+        float acc = (t.k_nw ? ldf(p0) : 0.f) * nw;
+        acc = fmaf(t.k_ne ? ldf(p0 + 1) : 0.f, ne, acc);
+        acc = fmaf(t.k_sw ? ldf(p1) : 0.f, sw, acc);
+        acc = fmaf(t.k_se ? ldf(p1 + 1) : 0.f, se, acc);
+        stf(o, acc);
     }
 }
 
@@ -159,10 +159,10 @@ __device__ __forceinline__ void emit_tap(const Workspace &ws, int plane0, int of
 }
 
 // MODE 0: g_flow only.  MODE 1: (g_flow) + emit tap lists.  MODE 2: (g_flow) + atomic g_x scatter.
-template <int NS, int MODE>
+template <int NS, int MODE, typename T>
 __global__ void __launch_bounds__(kBlock)
-warp_bwd_kernel(const float *__restrict__ x, const float *__restrict__ flow, const float *__restrict__ gout,
-                float *__restrict__ gx, float *__restrict__ gflow, Workspace ws, int N, int C, int H, int W,
+warp_bwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, const T *__restrict__ gout,
+                T *__restrict__ gx, float *__restrict__ gflow, Workspace ws, int N, int C, int H, int W,
                 int border, int rcp) {
     constexpr int PPB = kBlock / NS;
     __shared__ float red[2][NS][PPB];
@@ -189,25 +189,25 @@ warp_bwd_kernel(const float *__restrict__ x, const float *__restrict__ flow, con
             emit_tap(ws, b * HW, t.o_se, t.k_se, se, rem);
         }
         const size_t step = (size_t)NS * HW;
-        const float *gb = gout + ((size_t)b * C + cs) * HW + rem;
-        const float *p0 = x + ((size_t)b * C + cs) * HW + t.o_nw;
-        const float *p1 = p0 + W;
-        float *q0 = (MODE == 2) ? gx + ((size_t)b * C + cs) * HW + t.o_nw : nullptr;
+        const T *gb = gout + ((size_t)b * C + cs) * HW + rem;
+        const T *p0 = x + ((size_t)b * C + cs) * HW + t.o_nw;
+        const T *p1 = p0 + W;
+        T *q0 = (MODE == 2) ? gx + ((size_t)b * C + cs) * HW + t.o_nw : nullptr;
         if (gflow != nullptr || MODE == 2) {
 #pragma unroll 4
             for (int c = cs; c < C; c += NS, gb += step, p0 += step, p1 += step) {
-                const float go = __ldg(gb);
+                const float go = ldf(gb);
                 if (gflow != nullptr) {
-                    const float vnw = t.k_nw ? __ldg(p0) : 0.f, vne = t.k_ne ? __ldg(p0 + 1) : 0.f;
-                    const float vsw = t.k_sw ? __ldg(p1) : 0.f, vse = t.k_se ? __ldg(p1 + 1) : 0.f;
+                    const float vnw = t.k_nw ? ldf(p0) : 0.f, vne = t.k_ne ? ldf(p0 + 1) : 0.f;
+                    const float vsw = t.k_sw ? ldf(p1) : 0.f, vse = t.k_se ? ldf(p1 + 1) : 0.f;
                     gix = fmaf(go, fmaf(t.ey, vne - vnw, t.wy * (vse - vsw)), gix);
                     giy = fmaf(go, fmaf(t.ex, vsw - vnw, t.wx * (vse - vne)), giy);
                 }
                 if (MODE == 2) {
-                    if (t.k_nw) atomicAdd(q0, nw * go);
-                    if (t.k_ne) atomicAdd(q0 + 1, ne * go);
-                    if (t.k_sw) atomicAdd(q0 + W, sw * go);
-                    if (t.k_se) atomicAdd(q0 + W + 1, se * go);
+                    if (t.k_nw) atomic_addf(q0, nw * go);
+                    if (t.k_ne) atomic_addf(q0 + 1, ne * go);
+                    if (t.k_sw) atomic_addf(q0 + W, sw * go);
+                    if (t.k_se) atomic_addf(q0 + W + 1, se * go);
                     q0 += step;
                 }
             }
@@ -245,9 +245,9 @@ __device__ __forceinline__ void cswap(int &ka, float &wa, int &kb, float &wb) {
     }
 }
 
-template <int NS>
+template <int NS, typename T>
 __global__ void __launch_bounds__(kBlock)
-warp_gx_gather(const float *__restrict__ gout, float *__restrict__ gx, Workspace ws, int N, int C, int HW) {
+warp_gx_gather(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, int N, int C, int HW) {
     constexpr int PPB = kBlock / NS;
     // slice 0 of every pixel loads and sorts the tap list once; the other slices read it from here
     __shared__ int s_src[NS > 1 ? kSlots : 1][NS > 1 ? PPB : 1];
@@ -305,26 +305,27 @@ warp_gx_gather(const float *__restrict__ gout, float *__restrict__ gx, Workspace
     if (!live) return;
     const int b = p / HW, rem = p - b * HW;
     const size_t step = (size_t)NS * HW;
-    const float *plane = gout + ((size_t)b * C + cs) * HW;
-    float *o = gx + ((size_t)b * C + cs) * HW + rem;
+    const T *plane = gout + ((size_t)b * C + cs) * HW;
+    T *o = gx + ((size_t)b * C + cs) * HW + rem;
     // most targets receive <= 4 taps (exactly 4 for a smooth flow): the upper half is a rarely taken branch
 #pragma unroll 4
     for (int c = cs; c < C; c += NS, plane += step, o += step) {
         float acc = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            if (i < n) acc = fmaf(w[i], __ldg(plane + src[i]), acc);
+            if (i < n) acc = fmaf(w[i], ldf(plane + src[i]), acc);
         if (n > 4) {
 #pragma unroll
             for (int i = 4; i < kSlots; ++i)
-                if (i < n) acc = fmaf(w[i], __ldg(plane + src[i]), acc);
+                if (i < n) acc = fmaf(w[i], ldf(plane + src[i]), acc);
         }
-        *o = acc;
+        stf(o, acc);
     }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kBlock)
-warp_gx_overflow(const float *__restrict__ gout, float *__restrict__ gx, Workspace ws, int cap, int C, int HW) {
+warp_gx_overflow(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, int cap, int C, int HW) {
     const int n = min(ws.ovf_n[0], cap);
     const long total = (long)n * C;
     for (long it = (long)blockIdx.x * kBlock + threadIdx.x; it < total; it += (long)gridDim.x * kBlock) {
@@ -332,7 +333,7 @@ warp_gx_overflow(const float *__restrict__ gout, float *__restrict__ gx, Workspa
         const int tgt = ws.ovf_tgt[j];
         const int b = tgt / HW, trem = tgt - b * HW;
         const size_t plane = ((size_t)b * C + c) * HW;
-        atomicAdd(gx + plane + trem, ws.ovf_w[j] * __ldg(gout + plane + ws.ovf_src[j]));
+        atomic_addf(gx + plane + trem, ws.ovf_w[j] * ldf(gout + plane + ws.ovf_src[j]));
     }
 }
 
@@ -348,13 +349,14 @@ int pick_ns(int C, int N) {
 
 size_t warp_bwd_workspace_bytes(size_t N) { return ws_bytes(N); }
 
-int warp_fwd_f32(const float *x, const float *flow, float *out, int B, int C, int H, int W, int pad_mode,
-                 unsigned flags, cudaStream_t stream) {
+template <typename T>
+static int warp_fwd_t(const T *x, const float *flow, T *out, int B, int C, int H, int W, int pad_mode, unsigned flags,
+                      cudaStream_t stream) {
     const int N = B * H * W;
     const int border = pad_mode == USF_PAD_BORDER, rcp = (flags & USF_FLAG_COORD_RECIPROCAL) ? 1 : 0;
     const int ns = pick_ns(C, N);
     const int blocks = (N + kBlock / ns - 1) / (kBlock / ns);
-#define USF_LAUNCH(NS) warp_fwd_kernel<NS><<<blocks, kBlock, 0, stream>>>(x, flow, out, N, C, H, W, border, rcp)
+#define USF_LAUNCH(NS) warp_fwd_kernel<NS, T><<<blocks, kBlock, 0, stream>>>(x, flow, out, N, C, H, W, border, rcp)
     switch (ns) {
         case 8: USF_LAUNCH(8); break;
         case 4: USF_LAUNCH(4); break;
@@ -365,12 +367,11 @@ int warp_fwd_f32(const float *x, const float *flow, float *out, int B, int C, in
     return note_launch(cudaGetLastError());
 }
 
-template <int MODE>
-static cudaError_t launch_bwd(int ns, int blocks, const float *x, const float *flow, const float *gout,
-                              float *gx, float *gflow, Workspace ws, int N, int C, int H, int W, int border,
-                              int rcp, cudaStream_t stream) {
+template <int MODE, typename T>
+static cudaError_t launch_bwd(int ns, int blocks, const T *x, const float *flow, const T *gout, T *gx, float *gflow,
+                              Workspace ws, int N, int C, int H, int W, int border, int rcp, cudaStream_t stream) {
 #define USF_LAUNCH(NS) \
-    warp_bwd_kernel<NS, MODE><<<blocks, kBlock, 0, stream>>>(x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp)
+    warp_bwd_kernel<NS, MODE, T><<<blocks, kBlock, 0, stream>>>(x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp)
     switch (ns) {
         case 8: USF_LAUNCH(8); break;
         case 4: USF_LAUNCH(4); break;
@@ -381,30 +382,30 @@ static cudaError_t launch_bwd(int ns, int blocks, const float *x, const float *f
     return cudaGetLastError();
 }
 
-int warp_bwd_f32(const float *x, const float *flow, const float *gout, float *gx, float *gflow, int B, int C,
-                 int H, int W, int pad_mode, unsigned flags, void *workspace, size_t workspace_bytes,
-                 cudaStream_t stream) {
+template <typename T>
+static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float *gflow, int B, int C, int H, int W,
+                      int pad_mode, unsigned flags, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
     const int N = B * H * W, HW = H * W;
     const int border = pad_mode == USF_PAD_BORDER, rcp = (flags & USF_FLAG_COORD_RECIPROCAL) ? 1 : 0;
     const int ns = pick_ns(C, N);
     const int blocks = (N + kBlock / ns - 1) / (kBlock / ns);
     Workspace ws = {};
     if (gx == nullptr) {
-        return note_launch(launch_bwd<0>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
+        return note_launch(launch_bwd<0, T>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
     }
     if (flags & USF_FLAG_WARP_BWD_ATOMIC) {
-        cudaError_t e = cudaMemsetAsync(gx, 0, (size_t)N * C * sizeof(float), stream);
+        cudaError_t e = cudaMemsetAsync(gx, 0, (size_t)N * C * sizeof(T), stream);
         if (e != cudaSuccess) { note_cuda_error(e); return USF_ERR_CUDA; }
-        return note_launch(launch_bwd<2>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
+        return note_launch(launch_bwd<2, T>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
     }
     if (workspace == nullptr || workspace_bytes < ws_bytes((size_t)N) || ((uintptr_t)workspace & 15))
         return USF_ERR_WORKSPACE;
     ws = carve(workspace, (size_t)N);
     cudaError_t e = cudaMemsetAsync(ws.cnt, 0, cnt_bytes((size_t)N) + 16, stream);
     if (e != cudaSuccess) { note_cuda_error(e); return USF_ERR_CUDA; }
-    int st = note_launch(launch_bwd<1>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
+    int st = note_launch(launch_bwd<1, T>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
     if (st != USF_OK) return st;
-#define USF_LAUNCH(NS) warp_gx_gather<NS><<<blocks, kBlock, 0, stream>>>(gout, gx, ws, N, C, HW)
+#define USF_LAUNCH(NS) warp_gx_gather<NS, T><<<blocks, kBlock, 0, stream>>>(gout, gx, ws, N, C, HW)
     switch (ns) {
         case 8: USF_LAUNCH(8); break;
         case 4: USF_LAUNCH(4); break;
@@ -415,8 +416,28 @@ int warp_bwd_f32(const float *x, const float *flow, const float *gout, float *gx
     st = note_launch(cudaGetLastError());
     if (st != USF_OK) return st;
     // fixed grid (the entry count lives on the device): 8 CTAs per SM, grid-stride over entries x channels
-    warp_gx_overflow<<<148 * 8, kBlock, 0, stream>>>(gout, gx, ws, 4 * N, C, HW);
+    warp_gx_overflow<T><<<148 * 8, kBlock, 0, stream>>>(gout, gx, ws, 4 * N, C, HW);
     return note_launch(cudaGetLastError());
+}
+
+int warp_fwd_f32(const float *x, const float *flow, float *out, int B, int C, int H, int W, int pad_mode,
+                 unsigned flags, cudaStream_t stream) {
+    return warp_fwd_t<float>(x, flow, out, B, C, H, W, pad_mode, flags, stream);
+}
+int warp_bwd_f32(const float *x, const float *flow, const float *gout, float *gx, float *gflow, int B, int C,
+                 int H, int W, int pad_mode, unsigned flags, void *workspace, size_t workspace_bytes,
+                 cudaStream_t stream) {
+    return warp_bwd_t<float>(x, flow, gout, gx, gflow, B, C, H, W, pad_mode, flags, workspace, workspace_bytes, stream);
+}
+// bf16 storage of x / out / gout / gx; flow, coordinates, weights and all sums stay fp32
+int warp_fwd_bf16(const void *x, const float *flow, void *out, int B, int C, int H, int W, int pad_mode,
+                  unsigned flags, cudaStream_t stream) {
+    return warp_fwd_t<bf16>((const bf16 *)x, flow, (bf16 *)out, B, C, H, W, pad_mode, flags, stream);
+}
+int warp_bwd_bf16(const void *x, const float *flow, const void *gout, void *gx, float *gflow, int B, int C, int H,
+                  int W, int pad_mode, unsigned flags, void *workspace, size_t workspace_bytes, cudaStream_t stream) {
+    return warp_bwd_t<bf16>((const bf16 *)x, flow, (const bf16 *)gout, (bf16 *)gx, gflow, B, C, H, W, pad_mode, flags,
+                            workspace, workspace_bytes, stream);
 }
 
 }  // namespace usf

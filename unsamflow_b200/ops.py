@@ -9,6 +9,12 @@ import torch
 from . import _lib
 
 _PADS = {"border": _lib.PAD_BORDER, "zeros": _lib.PAD_ZEROS}
+_DTYPES = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+# bf16 storage / fp32 accumulate.  The C ABI handles bf16 for every shape with the direct kernels; above
+# this many pixels the host mirror instead widens to fp32, runs the tiled TMA kernels and narrows the
+# result (same arithmetic: bf16 -> fp32 is exact, sums are fp32, one rounding at the end), which is much
+# faster until native bf16 tiles land.
+BF16_NATIVE_MAX_PIXELS = 4096
 MAX_DISPLACEMENT = 4
 NUM_DISPLACEMENTS = 81
 
@@ -23,8 +29,8 @@ def _feat(t, name):
     if not t.is_cuda:
         raise RuntimeError(f"{name}: unsamflow_b200 runs on CUDA tensors only (got {t.device}); "
                            "there is no CPU path")
-    if t.dtype != torch.float32:
-        raise NotImplementedError(f"{name}: dtype {t.dtype} is not supported yet (float32 only)")
+    if t.dtype not in _DTYPES:
+        raise NotImplementedError(f"{name}: dtype {t.dtype} is not supported (float32 or bfloat16 storage)")
     return t.contiguous()
 
 
@@ -45,12 +51,20 @@ def corr_fwd(x1, x2, leaky_slope=None, out=None):
     L = _lib.load()
     x1, x2 = _feat(x1, "x1"), _feat(x2, "x2")
     _same(x1, x2, "x1", "x2")
+    if x1.dtype != x2.dtype:
+        raise ValueError(f"x1 is {x1.dtype} but x2 is {x2.dtype}")
     B, C, H, W = x1.shape
+    if x1.dtype == torch.bfloat16 and B * H * W > BF16_NATIVE_MAX_PIXELS:
+        wide = corr_fwd(x1.float(), x2.float(), leaky_slope)
+        if out is None:
+            return wide.to(torch.bfloat16)
+        out.copy_(wide)
+        return out
     if out is None:
         out = torch.empty((B, NUM_DISPLACEMENTS, H, W), dtype=x1.dtype, device=x1.device)
     with torch.cuda.device(x1.device):
         st = L.usf_corr_fwd(x1.data_ptr(), x2.data_ptr(), out.data_ptr(), B, C, H, W, MAX_DISPLACEMENT,
-                            _lib.F32, _flags(leaky=leaky_slope is not None),
+                            _DTYPES[x1.dtype], _flags(leaky=leaky_slope is not None),
                             float(leaky_slope or 0.0), _stream(x1))
     _lib.check(st, "usf_corr_fwd")
     return out
@@ -64,6 +78,20 @@ def corr_bwd(x1, x2, gout, need_gx1=True, need_gx2=True, gx1=None, gx2=None):
     B, C, H, W = x1.shape
     if tuple(gout.shape) != (B, NUM_DISPLACEMENTS, H, W):
         raise ValueError(f"grad_output.shape {tuple(gout.shape)} != {(B, NUM_DISPLACEMENTS, H, W)}")
+    if not (x1.dtype == x2.dtype == gout.dtype):
+        raise ValueError(f"dtype mismatch: {x1.dtype}, {x2.dtype}, {gout.dtype}")
+    if x1.dtype == torch.bfloat16 and B * H * W > BF16_NATIVE_MAX_PIXELS:
+        w1, w2 = corr_bwd(x1.float(), x2.float(), gout.float(), need_gx1, need_gx2)
+        res = []
+        for wide, dst, need in ((w1, gx1, need_gx1), (w2, gx2, need_gx2)):
+            if not need:
+                res.append(None)
+            elif dst is None:
+                res.append(wide.to(torch.bfloat16))
+            else:
+                dst.copy_(wide)
+                res.append(dst)
+        return tuple(res)
     if need_gx1 and gx1 is None:
         gx1 = torch.empty_like(x1)
     if need_gx2 and gx2 is None:
@@ -71,7 +99,7 @@ def corr_bwd(x1, x2, gout, need_gx1=True, need_gx2=True, gx1=None, gx2=None):
     with torch.cuda.device(x1.device):
         st = L.usf_corr_bwd(x1.data_ptr(), x2.data_ptr(), gout.data_ptr(),
                             gx1.data_ptr() if need_gx1 else None, gx2.data_ptr() if need_gx2 else None,
-                            B, C, H, W, MAX_DISPLACEMENT, _lib.F32, 0, _stream(x1))
+                            B, C, H, W, MAX_DISPLACEMENT, _DTYPES[x1.dtype], 0, _stream(x1))
     _lib.check(st, "usf_corr_bwd")
     return gx1, gx2
 
@@ -104,7 +132,7 @@ def warp_fwd(x, flow, pad="border", reciprocal=False, out=None):
     if out is None:
         out = torch.empty_like(x)
     with torch.cuda.device(x.device):
-        st = L.usf_warp_fwd(x.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, H, W, _pad(pad), _lib.F32,
+        st = L.usf_warp_fwd(x.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, H, W, _pad(pad), _DTYPES[x.dtype],
                             _flags(reciprocal=reciprocal), _stream(x))
     _lib.check(st, "usf_warp_fwd")
     return out
@@ -121,6 +149,8 @@ def warp_bwd(x, flow, gout, pad="border", need_gx=True, need_gflow=True, recipro
     L = _lib.load()
     x, gout = _feat(x, "x"), _feat(gout, "grad_output")
     _same(x, gout, "x", "grad_output")
+    if x.dtype != gout.dtype:
+        raise ValueError(f"x is {x.dtype} but grad_output is {gout.dtype}")
     flow = _flow(flow, x)
     B, C, H, W = x.shape
     flags = _flags(reciprocal=reciprocal, atomic=atomic)
@@ -138,7 +168,7 @@ def warp_bwd(x, flow, gout, pad="border", need_gx=True, need_gflow=True, recipro
     with torch.cuda.device(x.device):
         st = L.usf_warp_bwd(x.data_ptr(), flow.data_ptr(), gout.data_ptr(),
                             gx.data_ptr() if need_gx else None, gflow.data_ptr() if need_gflow else None,
-                            B, C, H, W, _pad(pad), _lib.F32, flags,
+                            B, C, H, W, _pad(pad), _DTYPES[x.dtype], flags,
                             ws.data_ptr() if ws is not None else None, ws_bytes, _stream(x))
     _lib.check(st, "usf_warp_bwd")
     return gx, gflow
