@@ -20,6 +20,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from unsamflow_b200 import hotpath, ops  # noqa: E402
 
 FLOW_KIND = "smooth"
+DTYPE = torch.float32
 KITTI = ["8x192x4x13", "8x128x8x26", "8x96x16x52", "8x64x32x104", "8x32x64x208"]
 
 
@@ -27,13 +28,13 @@ def build(op, shape, sigma):
     B, C, H, W = shape
     g = torch.Generator().manual_seed(1)
     dev = "cuda"
-    x1 = torch.randn(B, C, H, W, generator=g).to(dev)
-    x2 = torch.randn(B, C, H, W, generator=g).to(dev)
+    x1 = torch.randn(B, C, H, W, generator=g).to(dev).to(DTYPE)
+    x2 = torch.randn(B, C, H, W, generator=g).to(dev).to(DTYPE)
     if op == "corr_fwd":
-        out = torch.empty(B, 81, H, W, device=dev)
+        out = torch.empty(B, 81, H, W, device=dev, dtype=DTYPE)
         return (lambda: ops.corr_fwd(x1, x2, out=out)), hotpath.corr_fwd_bytes(*shape), hotpath.corr_fwd_flops(*shape), 1
     if op == "corr_bwd":
-        go = torch.randn(B, 81, H, W, generator=g).to(dev)
+        go = torch.randn(B, 81, H, W, generator=g).to(dev).to(DTYPE)
         g1, g2 = torch.empty_like(x1), torch.empty_like(x2)
         return (lambda: ops.corr_bwd(x1, x2, go, gx1=g1, gx2=g2)), hotpath.corr_bwd_bytes(*shape), 2 * hotpath.corr_fwd_flops(*shape), 2
     fl = (hotpath.synthetic_flow(B, H, W, sigma, g) if FLOW_KIND == "smooth"
@@ -64,11 +65,13 @@ def main():
     ap.add_argument("--sigma", type=float, default=3.0)
     ap.add_argument("--out", default="")
     ap.add_argument("--flow", default="smooth", choices=["smooth", "iid"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"], help="storage type of feature tensors")
     ap.add_argument("--preset", default="", choices=["", "sweep"],
                     help="sweep: BASELINE.json configs[4] (C=32..196, every pyramid level, B=1..64)")
     args = ap.parse_args()
-    global FLOW_KIND
+    global FLOW_KIND, DTYPE
     FLOW_KIND = args.flow
+    DTYPE = {"f32": torch.float32, "bf16": torch.bfloat16}[args.dtype]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     # wake the GPU up: a fresh box idles at ~120 MHz and takes a while to reach its boost clock
     burn = torch.randn(4096, 4096, device="cuda")
@@ -117,7 +120,7 @@ def main():
             mhz = pynvml.nvmlDeviceGetClockInfo(nvh, pynvml.NVML_CLOCK_SM) if nvh is not None else None
             row = {"op": op, "shape": s, "us": round(us, 2), "min_us": round(min(ts), 2), "launches": launches,
                    "GBps": round(nbytes / us / 1e3, 1), "TFLOPs": round(flops / us / 1e6, 2),
-                   "l2": "cold" if args.cold else "warm", "sm_mhz": mhz}
+                   "l2": "cold" if args.cold else "warm", "sm_mhz": mhz, "dtype": args.dtype}
             rows.append(row)
             print(json.dumps(row), flush=True)
     if args.out:

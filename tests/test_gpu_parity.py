@@ -443,7 +443,8 @@ def check_bf16(got, want, what):
     assert e1 <= BF16_L2 and e2 <= BF16_MAX, f"{what}: rel_l2={e1:.3e} max_norm={e2:.3e}"
 
 
-@pytest.mark.parametrize("shape", [(2, 64, 8, 26), (1, 33, 5, 11), (2, 32, 32, 104), (1, 96, 16, 52)],
+@pytest.mark.parametrize("shape", [(2, 64, 8, 26), (1, 33, 5, 11), (2, 32, 32, 104), (1, 96, 16, 52),
+                                   (8, 32, 64, 208), (2, 64, 48, 104), (1, 196, 24, 40), (3, 20, 9, 72)],
                          ids=lambda s: "x".join(map(str, s)))
 def test_bf16_corr_vs_oracle(usf, shape):
     from oracle import c_oracle

@@ -18,6 +18,7 @@ int warp_bwd_f32(const float *, const float *, const float *, float *, float *, 
                  unsigned, void *, size_t, cudaStream_t);
 size_t warp_bwd_workspace_bytes(size_t N);
 int corr_fwd_bf16(const void *, const void *, void *, int, int, int, int, unsigned, float, cudaStream_t);
+int corr_fwd_bf16_tiled(const void *, const void *, void *, int, int, int, int, unsigned, float, cudaStream_t);
 int corr_bwd_bf16(const void *, const void *, const void *, void *, void *, int, int, int, int, cudaStream_t);
 int warp_fwd_bf16(const void *, const float *, void *, int, int, int, int, int, unsigned, cudaStream_t);
 int warp_bwd_bf16(const void *, const float *, const void *, void *, float *, int, int, int, int, int, unsigned,
@@ -101,7 +102,13 @@ int usf_corr_fwd(const void *x1, const void *x2, void *out, int B, int C, int H,
     if (dtype == USF_F32)
         return corr_fwd_f32((const float *)x1, (const float *)x2, (float *)out, B, C, H, W, flags, leaky_slope,
                             (cudaStream_t)stream);
-    if (dtype == USF_BF16) return corr_fwd_bf16(x1, x2, out, B, C, H, W, flags, leaky_slope, (cudaStream_t)stream);
+    if (dtype == USF_BF16) {
+        if ((long)B * H * W > kDirectMaxPixels) {  // tiled TMA kernel when the shape allows (W % 8 == 0)
+            const int st = corr_fwd_bf16_tiled(x1, x2, out, B, C, H, W, flags, leaky_slope, (cudaStream_t)stream);
+            if (st != USF_ERR_UNSUPPORTED) return st;
+        }
+        return corr_fwd_bf16(x1, x2, out, B, C, H, W, flags, leaky_slope, (cudaStream_t)stream);
+    }
     return USF_ERR_BAD_ARG;
 }
 

@@ -54,7 +54,8 @@ def corr_fwd(x1, x2, leaky_slope=None, out=None):
     if x1.dtype != x2.dtype:
         raise ValueError(f"x1 is {x1.dtype} but x2 is {x2.dtype}")
     B, C, H, W = x1.shape
-    if x1.dtype == torch.bfloat16 and B * H * W > BF16_NATIVE_MAX_PIXELS:
+    if x1.dtype == torch.bfloat16 and B * H * W > BF16_NATIVE_MAX_PIXELS and W % 8 != 0:
+        # (W % 8 == 0 takes the native bf16 tiled TMA kernel, csrc/corr_fwd_bf16.cu)
         wide = corr_fwd(x1.float(), x2.float(), leaky_slope)
         if out is None:
             return wide.to(torch.bfloat16)
