@@ -499,3 +499,24 @@ def test_bf16_autograd_decoder_level(usf):
     check_bf16(out, c_oracle.corr_fwd(x1.float().numpy(), x2w_b), "out")
     assert a.grad.dtype == torch.bfloat16 and f.grad.dtype == torch.float32
     assert torch.isfinite(a.grad.float()).all() and torch.isfinite(f.grad).all()
+
+
+def test_empty_batch_and_nonfinite_flow(usf):
+    ops = usf.ops_mod
+    e = torch.zeros(0, 8, 6, 12).cuda()
+    assert tuple(ops.corr_fwd(e, e).shape) == (0, 81, 6, 12)
+    assert tuple(usf.flow_warp(e, torch.zeros(0, 2, 6, 12).cuda()).shape) == (0, 8, 6, 12)
+    # NaN / Inf / astronomically large flows must not fault and must only poison their own pixels
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(1, 4, 8, 16, generator=g).cuda()
+    go = torch.randn(1, 4, 8, 16, generator=g).cuda()
+    fl = torch.zeros(1, 2, 8, 16).cuda()
+    fl[0, 0, 0, 0], fl[0, 1, 1, 1], fl[0, 0, 2, 2], fl[0, 1, 3, 3] = float("nan"), float("inf"), 1e30, -1e30
+    for pad in ("zeros", "border"):
+        y = ops.warp_fwd(x, fl, pad)
+        gx, gf = ops.warp_bwd(x, fl, go, pad)
+        clean = torch.ones(8, 16, dtype=torch.bool).cuda()
+        for (r, c) in ((0, 0), (1, 1), (2, 2), (3, 3)):
+            clean[r, c] = False
+        assert torch.isfinite(y[0, :, clean]).all() and torch.isfinite(gf[0, :, clean]).all()
+        assert torch.allclose(y[0, :, clean], x[0, :, clean], atol=1e-5)   # zero flow elsewhere: identity

@@ -54,6 +54,8 @@ def corr_fwd(x1, x2, leaky_slope=None, out=None):
     if x1.dtype != x2.dtype:
         raise ValueError(f"x1 is {x1.dtype} but x2 is {x2.dtype}")
     B, C, H, W = x1.shape
+    if x1.numel() == 0:  # empty batch: the reference returns an empty cost volume too
+        return x1.new_empty((B, NUM_DISPLACEMENTS, H, W)) if out is None else out
     if x1.dtype == torch.bfloat16 and B * H * W > BF16_NATIVE_MAX_PIXELS and W % 8 != 0:
         # (W % 8 == 0 takes the native bf16 tiled TMA kernel, csrc/corr_fwd_bf16.cu)
         wide = corr_fwd(x1.float(), x2.float(), leaky_slope)
@@ -81,6 +83,8 @@ def corr_bwd(x1, x2, gout, need_gx1=True, need_gx2=True, gx1=None, gx2=None):
         raise ValueError(f"grad_output.shape {tuple(gout.shape)} != {(B, NUM_DISPLACEMENTS, H, W)}")
     if not (x1.dtype == x2.dtype == gout.dtype):
         raise ValueError(f"dtype mismatch: {x1.dtype}, {x2.dtype}, {gout.dtype}")
+    if x1.numel() == 0:
+        return (torch.empty_like(x1) if need_gx1 else None, torch.empty_like(x2) if need_gx2 else None)
     if x1.dtype == torch.bfloat16 and B * H * W > BF16_NATIVE_MAX_PIXELS:
         w1, w2 = corr_bwd(x1.float(), x2.float(), gout.float(), need_gx1, need_gx2)
         res = []
@@ -132,6 +136,8 @@ def warp_fwd(x, flow, pad="border", reciprocal=False, out=None):
         raise ValueError("flow_warp needs H, W >= 2 (the reference divides by size-1)")
     if out is None:
         out = torch.empty_like(x)
+    if x.numel() == 0:
+        return out
     with torch.cuda.device(x.device):
         st = L.usf_warp_fwd(x.data_ptr(), flow.data_ptr(), out.data_ptr(), B, C, H, W, _pad(pad), _DTYPES[x.dtype],
                             _flags(reciprocal=reciprocal), _stream(x))
@@ -154,6 +160,8 @@ def warp_bwd(x, flow, gout, pad="border", need_gx=True, need_gflow=True, recipro
         raise ValueError(f"x is {x.dtype} but grad_output is {gout.dtype}")
     flow = _flow(flow, x)
     B, C, H, W = x.shape
+    if x.numel() == 0:
+        return (torch.empty_like(x) if need_gx else None, torch.empty_like(flow) if need_gflow else None)
     flags = _flags(reciprocal=reciprocal, atomic=atomic)
     if need_gx and gx is None:
         gx = torch.empty_like(x)
