@@ -211,23 +211,62 @@ class HotPathStep:
         for op in (self.ops if ops_subset is None else ops_subset):
             op.fn()
 
+    def _streams(self, n):
+        pool = getattr(self, "_pool", None)
+        if pool is None:
+            pool = self._pool = []
+        while len(pool) < n:
+            pool.append(torch.cuda.Stream(device=self.device))
+        return pool[:n]
+
+    def _run_chain(self, chain, lanes):
+        """Run one direction's ops in order on the current stream; maximal runs of loss-side warps
+        ("lwarp_*": 4 photometric scales, independent of each other, losses/flow_loss.py:120-131) fan out
+        over `lanes` (one stream per scale) and join back."""
+        cur = torch.cuda.current_stream()
+        i = 0
+        while i < len(chain):
+            if not chain[i].name.startswith("lwarp") or not lanes:
+                chain[i].fn()
+                i += 1
+                continue
+            j = i
+            while j < len(chain) and chain[j].name.startswith("lwarp"):
+                j += 1
+            groups = {}
+            for op in chain[i:j]:
+                groups.setdefault(op.name.split(".")[1], []).append(op)   # by scale "S0".."S3"
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            joins = []
+            for lane, (_, grp) in zip(lanes, sorted(groups.items())):
+                lane.wait_event(fork)
+                with torch.cuda.stream(lane):
+                    for op in grp:
+                        op.fn()
+                ev = torch.cuda.Event()
+                ev.record(lane)
+                joins.append(ev)
+            for ev in joins:
+                cur.wait_event(ev)
+            i = j
+
     def run_concurrent(self, per_stream):
         """Run {"d12": [ops], "d21": [ops]} on two streams forked from / joined to the current
         stream (works under CUDA-graph capture).  PWCLite.forward calls its two decoders back to back
-        (models/pwclite.py:430-432) although they are independent; this is that overlap."""
+        (models/pwclite.py:430-432) although they are independent; this is that overlap.  Inside each
+        direction the four loss scales additionally fan out over their own streams."""
         main = torch.cuda.current_stream()
-        if getattr(self, "_side", None) is None:
-            self._side = torch.cuda.Stream(device=self.device)
+        pool = self._streams(1 + 2 * NUM_LOSS_SCALES)
+        side, lanes_a, lanes_b = pool[0], pool[1:1 + NUM_LOSS_SCALES], pool[1 + NUM_LOSS_SCALES:]
         fork = torch.cuda.Event()
         fork.record(main)
-        self._side.wait_event(fork)
-        with torch.cuda.stream(self._side):
-            for op in per_stream.get("d21", []):
-                op.fn()
-        for op in per_stream.get("d12", []):
-            op.fn()
+        side.wait_event(fork)
+        with torch.cuda.stream(side):
+            self._run_chain(per_stream.get("d21", []), lanes_b)
+        self._run_chain(per_stream.get("d12", []), lanes_a)
         join = torch.cuda.Event()
-        join.record(self._side)
+        join.record(side)
         main.wait_event(join)
 
     def split_around(self, dom):
