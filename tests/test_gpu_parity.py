@@ -105,6 +105,9 @@ CORR_SHAPES = [
     (1, 128, 12, 26), (1, 64, 48, 104), (1, 192, 3, 10), (1, 96, 20, 44), (1, 192, 5, 11),
     # microbench sweep corner: C not a multiple of 8, C tiny, single pixel row/col
     (1, 196, 9, 33), (2, 3, 17, 70), (1, 1, 8, 32), (1, 40, 1, 5), (1, 33, 7, 1),
+    # whole-image-in-shared-memory kernels (H*W <= 256): pair / single pixel variants, ragged channel groups,
+    # more channels than one shared-memory chunk holds
+    (3, 20, 6, 14), (2, 9, 16, 16), (8, 128, 8, 26), (2, 12, 4, 13), (1, 200, 8, 32), (2, 130, 15, 17), (17, 100, 8, 32),
 ]
 
 
@@ -152,6 +155,12 @@ def test_corr_nullable_grads_and_unaligned_views(usf):
     none, g2 = ops.corr_bwd(x1.cuda(), x2.cuda(), go.cuda(), need_gx1=False)
     assert none is None
     check(g2, o2, "gx2 only")
+    # the same on a whole-image (H*W <= 256) shape, where one CTA normally computes both gradients
+    y1, y2 = torch.randn(2, 24, 8, 26, generator=g), torch.randn(2, 24, 8, 26, generator=g)
+    gy = torch.randn(2, 81, 8, 26, generator=g)
+    s1, s2 = c_oracle.corr_bwd(y1.numpy(), y2.numpy(), gy.numpy())
+    check(ops.corr_bwd(y1.cuda(), y2.cuda(), gy.cuda(), need_gx2=False)[0], s1, "small gx1 only")
+    check(ops.corr_bwd(y1.cuda(), y2.cuda(), gy.cuda(), need_gx1=False)[1], s2, "small gx2 only")
     # storage offset of 4 bytes -> the 16-byte vector path must not be taken
     buf = torch.zeros(x1.numel() + 1).cuda()
     buf[1:] = x1.flatten().cuda()
@@ -170,6 +179,9 @@ def test_corr_fused_leaky_relu(usf):
     plain = ops.corr_fwd(x1, x2)
     fused = ops.corr_fwd(x1, x2, leaky_slope=0.1)
     assert torch.equal(fused, torch.nn.functional.leaky_relu(plain, 0.1))
+    for shape in [(2, 128, 8, 26), (2, 192, 4, 13)]:
+        y1, y2 = torch.randn(shape, generator=g).cuda(), torch.randn(shape, generator=g).cuda()
+        assert torch.equal(ops.corr_fwd(y1, y2, leaky_slope=0.1), torch.nn.functional.leaky_relu(ops.corr_fwd(y1, y2), 0.1))
 
 
 WARP_SHAPES = [
@@ -399,17 +411,20 @@ def test_cuda_graph_capture_of_a_step(usf):
 
 
 def test_fallback_kernels_in_a_subprocess(usf):
-    """USF_DISABLE_TMA=1 + USF_DIRECT_MAX_PIXELS=0 force the cp.async kernels that normally only serve
-    large odd-width shapes; they must pass the same golden / oracle checks."""
+    """USF_DISABLE_TMA=1 + USF_DIRECT_MAX_PIXELS=0 + USF_SMALL_MAX_HW=0 force the cp.async kernels that normally
+    only serve large odd-width shapes; USF_SMALL_MAX_HW=0 alone sends the tiny levels to the direct kernels.
+    Both must pass the same golden / oracle checks."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, USF_DISABLE_TMA="1", USF_DIRECT_MAX_PIXELS="0")
     here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(here, "test_gpu_parity.py"),
-                        "-k", "golden or corr_vs_oracle or nullable"], env=env, capture_output=True, text=True,
-                       timeout=900)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    for extra in ({"USF_DISABLE_TMA": "1", "USF_DIRECT_MAX_PIXELS": "0", "USF_SMALL_MAX_HW": "0"},
+                  {"USF_SMALL_MAX_HW": "0"}):
+        env = dict(os.environ, **extra)
+        r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu",
+                            os.path.join(here, "test_gpu_parity.py"), "-k", "golden or corr_vs_oracle or nullable"],
+                           env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, str(extra) + r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_corr_kernels_are_bit_deterministic_under_load(usf):

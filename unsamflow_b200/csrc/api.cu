@@ -24,6 +24,13 @@ int warp_fwd_bf16(const void *, const float *, void *, int, int, int, int, int, 
 int warp_bwd_bf16(const void *, const float *, const void *, void *, float *, int, int, int, int, int, unsigned,
                   void *, size_t, cudaStream_t);
 
+int corr_fwd_small_f32(const float *, const float *, float *, int, int, int, int, unsigned, float, cudaStream_t);
+int corr_bwd_small_f32(const float *, const float *, const float *, float *, float *, int, int, int, int,
+                       cudaStream_t);
+int corr_fwd_small_bf16(const void *, const void *, void *, int, int, int, int, unsigned, float, cudaStream_t);
+int corr_bwd_small_bf16(const void *, const void *, const void *, void *, void *, int, int, int, int, cudaStream_t);
+bool corr_small_applies(int H, int W);  // whole image <= 256 pixels: corr_small.cu
+
 long kDirectMaxPixels = [] {
     const char *e = getenv("USF_DIRECT_MAX_PIXELS");
     return e ? atol(e) : 4096L;
@@ -99,6 +106,14 @@ int usf_corr_fwd(const void *x1, const void *x2, void *out, int B, int C, int H,
     if (!x1 || !x2 || !out || max_disp != kMaxDisp) return USF_ERR_BAD_ARG;
     if (flags & ~USF_FLAG_LEAKY_RELU) return USF_ERR_BAD_ARG;
     if (int st = check_dims(B, C, H, W, kK)) return st;
+    if (corr_small_applies(H, W)) {
+        if (dtype == USF_F32)
+            return corr_fwd_small_f32((const float *)x1, (const float *)x2, (float *)out, B, C, H, W, flags,
+                                      leaky_slope, (cudaStream_t)stream);
+        if (dtype == USF_BF16)
+            return corr_fwd_small_bf16(x1, x2, out, B, C, H, W, flags, leaky_slope, (cudaStream_t)stream);
+        return USF_ERR_BAD_ARG;
+    }
     if (dtype == USF_F32)
         return corr_fwd_f32((const float *)x1, (const float *)x2, (float *)out, B, C, H, W, flags, leaky_slope,
                             (cudaStream_t)stream);
@@ -117,6 +132,13 @@ int usf_corr_bwd(const void *x1, const void *x2, const void *gout, void *gx1, vo
     if (!x1 || !x2 || !gout || max_disp != kMaxDisp || flags != 0) return USF_ERR_BAD_ARG;
     if (int st = check_dims(B, C, H, W, kK)) return st;
     if (!gx1 && !gx2) return USF_OK;
+    if (corr_small_applies(H, W)) {
+        if (dtype == USF_F32)
+            return corr_bwd_small_f32((const float *)x1, (const float *)x2, (const float *)gout, (float *)gx1,
+                                      (float *)gx2, B, C, H, W, (cudaStream_t)stream);
+        if (dtype == USF_BF16) return corr_bwd_small_bf16(x1, x2, gout, gx1, gx2, B, C, H, W, (cudaStream_t)stream);
+        return USF_ERR_BAD_ARG;
+    }
     if (dtype == USF_F32)
         return corr_bwd_f32((const float *)x1, (const float *)x2, (const float *)gout, (float *)gx1,
                             (float *)gx2, B, C, H, W, (cudaStream_t)stream);

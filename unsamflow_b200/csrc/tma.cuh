@@ -95,6 +95,21 @@ __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *m
         "l"((uint64_t)map), "r"(s32(bar)), "r"(x), "r"(y), "r"(c), "r"(b)
         : "memory");
 }
+// 2-D box load: coordinates are (column, row)
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::
+            "r"(s32(smem_dst)),
+        "l"((uint64_t)map), "r"(s32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+// 1-D bulk copy global -> shared (no tensor map): 16-byte aligned source, destination and size
+__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::
+                     "r"(s32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(s32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];\n" ::"l"((uint64_t)map) : "memory");
 }
