@@ -21,6 +21,10 @@
 //   warp_gx_overflow    targets hit by more than kSlots taps (e.g. a region clipped onto the image
 //                       border) keep their first kSlots taps in the list; the rest go through a
 //                       side list handled with float atomics after the gather has written g_x.
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace usf {
@@ -81,34 +85,55 @@ __device__ __forceinline__ float ldp(const float *__restrict__ base, int off, bo
 }
 
 // ---------------------------------------------------------------------------------------------
+// Persistent over pixel blocks (grid = resident CTAs when the level has more blocks than that): the flow of
+// the NEXT block is requested before the taps of the current one are consumed, so a thread's life is one
+// memory round trip per pixel instead of two back-to-back (flow, then taps).  With cold inputs -- the normal
+// case inside a training step, whose working set is far larger than L2 -- that serialised pair was the
+// limiter (1.5 TB/s on the 256x832 loss-side warp).
 template <int NS, typename T>
 __global__ void __launch_bounds__(kBlock)
 warp_fwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, T *__restrict__ out, int N,
                 int C, int H, int W, int border, int rcp) {
     constexpr int PPB = kBlock / NS;
-    const int p = blockIdx.x * PPB + (threadIdx.x % PPB);
-    const int cs = threadIdx.x / PPB;
-    if (p >= N) return;
-    const int HW = H * W;
-    const int b = p / HW, rem = p - b * HW;
-    const int y = rem / W, xo = rem - y * W;
-    const float u = __ldg(flow + (size_t)b * 2 * HW + rem);
-    const float v = __ldg(flow + (size_t)b * 2 * HW + HW + rem);
-    const Taps t = make_taps(y, xo, u, v, H, W, border, rcp);
-    const float nw = t.ex * t.ey, ne = t.wx * t.ey, sw = t.ex * t.wy, se = t.wx * t.wy;
-    // two row pointers (taps nw/ne and sw/se are neighbours) bumped by one slice stride per channel:
-    // no per-tap address arithmetic in the loop; out-of-image taps are predicated off, never read
-    const size_t step = (size_t)NS * HW;
-    const T *p0 = x + ((size_t)b * C + cs) * HW + t.o_nw;
-    const T *p1 = p0 + W;
-    T *o = out + ((size_t)b * C + cs) * HW + rem;
-#pragma unroll 4
-    for (int c = cs; c < C; c += NS, p0 += step, p1 += step, o += step) {
-        float acc = (t.k_nw ? ldf(p0) : 0.f) * nw;
-        acc = fmaf(t.k_ne ? ldf(p0 + 1) : 0.f, ne, acc);
-        acc = fmaf(t.k_sw ? ldf(p1) : 0.f, sw, acc);
-        acc = fmaf(t.k_se ? ldf(p1 + 1) : 0.f, se, acc);
-        stf(o, acc);
+    constexpr int UN = NS >= 4 ? 8 : 4;  // channels in flight per thread
+    const int pl = threadIdx.x % PPB, cs = threadIdx.x / PPB;
+    const int HW = H * W, stride = gridDim.x * PPB;
+    int p = blockIdx.x * PPB + pl;
+    float u = 0.f, v = 0.f;
+    if (p < N) {
+        const int b = p / HW, rem = p - b * HW;
+        u = __ldg(flow + (size_t)b * 2 * HW + rem);
+        v = __ldg(flow + (size_t)b * 2 * HW + HW + rem);
+    }
+    while (p < N) {
+        const int b = p / HW, rem = p - b * HW;
+        const int y = rem / W, xo = rem - y * W;
+        const int pn = p + stride;
+        float un = 0.f, vn = 0.f;
+        if (pn < N) {
+            const int bn = pn / HW, remn = pn - bn * HW;
+            un = __ldg(flow + (size_t)bn * 2 * HW + remn);
+            vn = __ldg(flow + (size_t)bn * 2 * HW + HW + remn);
+        }
+        const Taps t = make_taps(y, xo, u, v, H, W, border, rcp);
+        const float nw = t.ex * t.ey, ne = t.wx * t.ey, sw = t.ex * t.wy, se = t.wx * t.wy;
+        // two row pointers (taps nw/ne and sw/se are neighbours) bumped by one slice stride per channel:
+        // no per-tap address arithmetic in the loop; out-of-image taps are predicated off, never read
+        const size_t step = (size_t)NS * HW;
+        const T *p0 = x + ((size_t)b * C + cs) * HW + t.o_nw;
+        const T *p1 = p0 + W;
+        T *o = out + ((size_t)b * C + cs) * HW + rem;
+#pragma unroll UN
+        for (int c = cs; c < C; c += NS, p0 += step, p1 += step, o += step) {
+            float acc = (t.k_nw ? ldf(p0) : 0.f) * nw;
+            acc = fmaf(t.k_ne ? ldf(p0 + 1) : 0.f, ne, acc);
+            acc = fmaf(t.k_sw ? ldf(p1) : 0.f, sw, acc);
+            acc = fmaf(t.k_se ? ldf(p1 + 1) : 0.f, se, acc);
+            stf(o, acc);
+        }
+        p = pn;
+        u = un;
+        v = vn;
     }
 }
 
@@ -338,16 +363,34 @@ warp_gx_overflow(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, i
 }
 
 // Channel slices per pixel: enough threads to fill the chip (~one full wave of 148 x 2048), but as few
-// slices as possible because every slice repeats the coordinate arithmetic (two IEEE divisions).
+// slices as possible because every slice repeats the coordinate arithmetic (two IEEE divisions).  Small
+// levels end up with 4-8 channels per thread: their cost is the depth of the dependent-load chain.
 int pick_ns(int C, int N) {
     int ns = 1;
-    while (ns < 8 && (long)N * ns < 148L * 2048 && C >= 8 * ns) ns *= 2;
+    const long wave = 148L * 2048;
+    while (ns < 32 && C >= 8 * ns && (ns < 8 ? (long)N * ns < wave : (long)N * ns * 2 <= wave)) ns *= 2;
     return ns;
 }
 
 }  // namespace
 
 size_t warp_bwd_workspace_bytes(size_t N) { return ws_bytes(N); }
+
+// CTAs of `kernel` that fit on the device at once (cached per kernel and device)
+static int resident_ctas(const void *kernel) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, int> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148 * 4;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(kernel, dev);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    int per_sm = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+    return cache[key] = per_sm * sms;
+}
 
 template <typename T>
 static int warp_fwd_t(const T *x, const float *flow, T *out, int B, int C, int H, int W, int pad_mode, unsigned flags,
@@ -356,8 +399,14 @@ static int warp_fwd_t(const T *x, const float *flow, T *out, int B, int C, int H
     const int border = pad_mode == USF_PAD_BORDER, rcp = (flags & USF_FLAG_COORD_RECIPROCAL) ? 1 : 0;
     const int ns = pick_ns(C, N);
     const int blocks = (N + kBlock / ns - 1) / (kBlock / ns);
-#define USF_LAUNCH(NS) warp_fwd_kernel<NS, T><<<blocks, kBlock, 0, stream>>>(x, flow, out, N, C, H, W, border, rcp)
+#define USF_LAUNCH(NS)                                                                      \
+    {                                                                                       \
+        const int res = resident_ctas((const void *)warp_fwd_kernel<NS, T>);                \
+        warp_fwd_kernel<NS, T><<<blocks < res ? blocks : res, kBlock, 0, stream>>>(x, flow, out, N, C, H, W, border, rcp); \
+    }
     switch (ns) {
+        case 32: USF_LAUNCH(32); break;
+        case 16: USF_LAUNCH(16); break;
         case 8: USF_LAUNCH(8); break;
         case 4: USF_LAUNCH(4); break;
         case 2: USF_LAUNCH(2); break;
@@ -373,6 +422,8 @@ static cudaError_t launch_bwd(int ns, int blocks, const T *x, const float *flow,
 #define USF_LAUNCH(NS) \
     warp_bwd_kernel<NS, MODE, T><<<blocks, kBlock, 0, stream>>>(x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp)
     switch (ns) {
+        case 32: USF_LAUNCH(32); break;
+        case 16: USF_LAUNCH(16); break;
         case 8: USF_LAUNCH(8); break;
         case 4: USF_LAUNCH(4); break;
         case 2: USF_LAUNCH(2); break;
@@ -407,6 +458,8 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
     if (st != USF_OK) return st;
 #define USF_LAUNCH(NS) warp_gx_gather<NS, T><<<blocks, kBlock, 0, stream>>>(gout, gx, ws, N, C, HW)
     switch (ns) {
+        case 32: USF_LAUNCH(32); break;
+        case 16: USF_LAUNCH(16); break;
         case 8: USF_LAUNCH(8); break;
         case 4: USF_LAUNCH(4); break;
         case 2: USF_LAUNCH(2); break;
@@ -415,8 +468,11 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
 #undef USF_LAUNCH
     st = note_launch(cudaGetLastError());
     if (st != USF_OK) return st;
-    // fixed grid (the entry count lives on the device): 8 CTAs per SM, grid-stride over entries x channels
-    warp_gx_overflow<T><<<148 * 8, kBlock, 0, stream>>>(gout, gx, ws, 4 * N, C, HW);
+    // fixed grid (the entry count lives on the device), sized for the worst case of this shape: up to 8 CTAs
+    // per SM, grid-stride over entries x channels
+    long ovf_blocks = ((long)4 * N * C + 16L * kBlock - 1) / (16L * kBlock);
+    ovf_blocks = ovf_blocks < 16 ? 16 : (ovf_blocks > 148 * 8 ? 148 * 8 : ovf_blocks);
+    warp_gx_overflow<T><<<(int)ovf_blocks, kBlock, 0, stream>>>(gout, gx, ws, 4 * N, C, HW);
     return note_launch(cudaGetLastError());
 }
 
