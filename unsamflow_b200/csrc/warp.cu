@@ -33,6 +33,26 @@ namespace {
 constexpr int kBlock = 256;
 constexpr int kSlots = 8;  // list capacity per target pixel
 
+// Division by a launch-time constant: q = floor(n / d) for 0 <= n < 2^31 as one IMAD.HI + add + shift
+// (M = ceil(2^(32+L) / d) = 2^32 + m with L = ceil(log2 d); the integer divides were a quarter of all
+// instructions of the 3-channel loss-side warp).
+struct FastDiv {
+    unsigned m;
+    int L;
+    int d;
+    __device__ __forceinline__ int div(int n) const { return (int)((__umulhi(m, (unsigned)n) + (unsigned)n) >> L); }
+};
+inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = d;
+    f.L = 0;
+    while ((1u << f.L) < (unsigned)d) ++f.L;
+    const unsigned long long one = 1ull << (32 + f.L);
+    const unsigned long long M = one / (unsigned)d + ((one % (unsigned)d) ? 1 : 0);
+    f.m = (unsigned)(M - (1ull << 32));
+    return f;
+}
+
 struct Taps {
     int o_nw, o_ne, o_sw, o_se;      // offsets inside one H*W plane (valid only if ok_*)
     bool k_nw, k_ne, k_sw, k_se;     // tap inside the image
@@ -93,7 +113,7 @@ __device__ __forceinline__ float ldp(const float *__restrict__ base, int off, bo
 template <int NS, typename T>
 __global__ void __launch_bounds__(kBlock)
 warp_fwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, T *__restrict__ out, int N,
-                int C, int H, int W, int border, int rcp) {
+                int C, int H, int W, int border, int rcp, FastDiv dHW, FastDiv dW) {
     constexpr int PPB = kBlock / NS;
     constexpr int UN = NS >= 4 ? 8 : 4;  // channels in flight per thread
     const int pl = threadIdx.x % PPB, cs = threadIdx.x / PPB;
@@ -101,17 +121,17 @@ warp_fwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, T *__re
     int p = blockIdx.x * PPB + pl;
     float u = 0.f, v = 0.f;
     if (p < N) {
-        const int b = p / HW, rem = p - b * HW;
+        const int b = dHW.div(p), rem = p - b * HW;
         u = __ldg(flow + (size_t)b * 2 * HW + rem);
         v = __ldg(flow + (size_t)b * 2 * HW + HW + rem);
     }
     while (p < N) {
-        const int b = p / HW, rem = p - b * HW;
-        const int y = rem / W, xo = rem - y * W;
+        const int b = dHW.div(p), rem = p - b * HW;
+        const int y = dW.div(rem), xo = rem - y * W;
         const int pn = p + stride;
         float un = 0.f, vn = 0.f;
         if (pn < N) {
-            const int bn = pn / HW, remn = pn - bn * HW;
+            const int bn = dHW.div(pn), remn = pn - bn * HW;
             un = __ldg(flow + (size_t)bn * 2 * HW + remn);
             vn = __ldg(flow + (size_t)bn * 2 * HW + HW + remn);
         }
@@ -188,79 +208,100 @@ template <int NS, int MODE, typename T>
 __global__ void __launch_bounds__(kBlock)
 warp_bwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, const T *__restrict__ gout,
                 T *__restrict__ gx, float *__restrict__ gflow, Workspace ws, int N, int C, int H, int W,
-                int border, int rcp) {
+                int border, int rcp, FastDiv dHW, FastDiv dW) {
     constexpr int PPB = kBlock / NS;
+    constexpr int UN = NS >= 4 ? 8 : 4;  // channels in flight per thread
     __shared__ float red[2][NS][PPB];
-    const int pl = threadIdx.x % PPB;
-    const int p = blockIdx.x * PPB + pl;
-    const int cs = threadIdx.x / PPB;
-    const bool live = p < N;
-    const int HW = H * W;
-    float gix = 0.f, giy = 0.f;
-    int b = 0, rem = 0;
-    Taps t;
-    if (live) {
-        b = p / HW;
-        rem = p - b * HW;
-        const int y = rem / W, xo = rem - y * W;
-        const float u = __ldg(flow + (size_t)b * 2 * HW + rem);
-        const float v = __ldg(flow + (size_t)b * 2 * HW + HW + rem);
-        t = make_taps(y, xo, u, v, H, W, border, rcp);
-        const float nw = t.ex * t.ey, ne = t.wx * t.ey, sw = t.ex * t.wy, se = t.wx * t.wy;
-        if (MODE == 1 && cs == 0) {
-            emit_tap(ws, b * HW, t.o_nw, t.k_nw, nw, rem);
-            emit_tap(ws, b * HW, t.o_ne, t.k_ne, ne, rem);
-            emit_tap(ws, b * HW, t.o_sw, t.k_sw, sw, rem);
-            emit_tap(ws, b * HW, t.o_se, t.k_se, se, rem);
+    const int pl = threadIdx.x % PPB, cs = threadIdx.x / PPB;
+    const int HW = H * W, stride = gridDim.x * PPB;
+    // persistent over pixel blocks, flow of the next block prefetched (see warp_fwd_kernel); the loop bound
+    // is uniform over the CTA because of the barriers in the reduction
+    int p = blockIdx.x * PPB + pl;
+    float u = 0.f, v = 0.f;
+    if (p < N) {
+        const int b = dHW.div(p), rem = p - b * HW;
+        u = __ldg(flow + (size_t)b * 2 * HW + rem);
+        v = __ldg(flow + (size_t)b * 2 * HW + HW + rem);
+    }
+    for (int base = blockIdx.x * PPB; base < N; base += stride, p += stride) {
+        const bool live = p < N;
+        const int pn = p + stride;
+        float un = 0.f, vn = 0.f;
+        if (pn < N) {
+            const int bn = dHW.div(pn), remn = pn - bn * HW;
+            un = __ldg(flow + (size_t)bn * 2 * HW + remn);
+            vn = __ldg(flow + (size_t)bn * 2 * HW + HW + remn);
         }
-        const size_t step = (size_t)NS * HW;
-        const T *gb = gout + ((size_t)b * C + cs) * HW + rem;
-        const T *p0 = x + ((size_t)b * C + cs) * HW + t.o_nw;
-        const T *p1 = p0 + W;
-        T *q0 = (MODE == 2) ? gx + ((size_t)b * C + cs) * HW + t.o_nw : nullptr;
-        if (gflow != nullptr || MODE == 2) {
-#pragma unroll 4
-            for (int c = cs; c < C; c += NS, gb += step, p0 += step, p1 += step) {
-                const float go = ldf(gb);
-                if (gflow != nullptr) {
-                    const float vnw = t.k_nw ? ldf(p0) : 0.f, vne = t.k_ne ? ldf(p0 + 1) : 0.f;
-                    const float vsw = t.k_sw ? ldf(p1) : 0.f, vse = t.k_se ? ldf(p1 + 1) : 0.f;
-                    gix = fmaf(go, fmaf(t.ey, vne - vnw, t.wy * (vse - vsw)), gix);
-                    giy = fmaf(go, fmaf(t.ex, vsw - vnw, t.wx * (vse - vne)), giy);
-                }
-                if (MODE == 2) {
-                    if (t.k_nw) atomic_addf(q0, nw * go);
-                    if (t.k_ne) atomic_addf(q0 + 1, ne * go);
-                    if (t.k_sw) atomic_addf(q0 + W, sw * go);
-                    if (t.k_se) atomic_addf(q0 + W + 1, se * go);
-                    q0 += step;
+        float gix = 0.f, giy = 0.f;
+        int b = 0, rem = 0;
+        Taps t;
+        if (live) {
+            b = dHW.div(p);
+            rem = p - b * HW;
+            const int y = dW.div(rem), xo = rem - y * W;
+            t = make_taps(y, xo, u, v, H, W, border, rcp);
+            const float nw = t.ex * t.ey, ne = t.wx * t.ey, sw = t.ex * t.wy, se = t.wx * t.wy;
+            if (MODE == 1 && cs == 0) {
+                emit_tap(ws, b * HW, t.o_nw, t.k_nw, nw, rem);
+                emit_tap(ws, b * HW, t.o_ne, t.k_ne, ne, rem);
+                emit_tap(ws, b * HW, t.o_sw, t.k_sw, sw, rem);
+                emit_tap(ws, b * HW, t.o_se, t.k_se, se, rem);
+            }
+            const size_t step = (size_t)NS * HW;
+            const T *gb = gout + ((size_t)b * C + cs) * HW + rem;
+            const T *p0 = x + ((size_t)b * C + cs) * HW + t.o_nw;
+            const T *p1 = p0 + W;
+            T *q0 = (MODE == 2) ? gx + ((size_t)b * C + cs) * HW + t.o_nw : nullptr;
+            if (gflow != nullptr || MODE == 2) {
+#pragma unroll UN
+                for (int c = cs; c < C; c += NS, gb += step, p0 += step, p1 += step) {
+                    const float go = ldf(gb);
+                    if (gflow != nullptr) {
+                        const float vnw = t.k_nw ? ldf(p0) : 0.f, vne = t.k_ne ? ldf(p0 + 1) : 0.f;
+                        const float vsw = t.k_sw ? ldf(p1) : 0.f, vse = t.k_se ? ldf(p1 + 1) : 0.f;
+                        gix = fmaf(go, fmaf(t.ey, vne - vnw, t.wy * (vse - vsw)), gix);
+                        giy = fmaf(go, fmaf(t.ex, vsw - vnw, t.wx * (vse - vne)), giy);
+                    }
+                    if (MODE == 2) {
+                        if (t.k_nw) atomic_addf(q0, nw * go);
+                        if (t.k_ne) atomic_addf(q0 + 1, ne * go);
+                        if (t.k_sw) atomic_addf(q0 + W, sw * go);
+                        if (t.k_se) atomic_addf(q0 + W + 1, se * go);
+                        q0 += step;
+                    }
                 }
             }
         }
-    }
-    if (gflow == nullptr) return;
-    if (NS > 1) {
-        red[0][cs][pl] = gix;
-        red[1][cs][pl] = giy;
-        __syncthreads();
-        if (cs != 0 || !live) return;
-        gix = red[0][0][pl];
-        giy = red[1][0][pl];
+        u = un;
+        v = vn;
+        if (gflow == nullptr) continue;
+        bool writer = live;
+        if (NS > 1) {
+            red[0][cs][pl] = gix;
+            red[1][cs][pl] = giy;
+            __syncthreads();
+            writer = live && cs == 0;
+            if (writer) {
+                gix = red[0][0][pl];
+                giy = red[1][0][pl];
 #pragma unroll
-        for (int s = 1; s < NS; ++s) {
-            gix += red[0][s][pl];
-            giy += red[1][s][pl];
+                for (int s = 1; s < NS; ++s) {
+                    gix += red[0][s][pl];
+                    giy += red[1][s][pl];
+                }
+            }
+            __syncthreads();  // red is rewritten by the next pixel block
         }
-    } else if (!live) {
-        return;
+        if (writer) {
+            // grid_sampler backward: ggrid = mult * gi; norm_grid backward: (g / (size-1)) * 2
+            const float sx = (float)(W - 1), sy = (float)(H - 1);
+            const float gxn = __fmul_rn(t.mx, gix), gyn = __fmul_rn(t.my, giy);
+            const float dfx = rcp ? __fmul_rn(gxn, __fdiv_rn(1.0f, sx)) : __fdiv_rn(gxn, sx);
+            const float dfy = rcp ? __fmul_rn(gyn, __fdiv_rn(1.0f, sy)) : __fdiv_rn(gyn, sy);
+            gflow[(size_t)b * 2 * HW + rem] = __fmul_rn(dfx, 2.0f);
+            gflow[(size_t)b * 2 * HW + HW + rem] = __fmul_rn(dfy, 2.0f);
+        }
     }
-    // grid_sampler backward: ggrid = mult * gi; norm_grid backward: (g / (size-1)) * 2
-    const float sx = (float)(W - 1), sy = (float)(H - 1);
-    const float gxn = __fmul_rn(t.mx, gix), gyn = __fmul_rn(t.my, giy);
-    const float dfx = rcp ? __fmul_rn(gxn, __fdiv_rn(1.0f, sx)) : __fdiv_rn(gxn, sx);
-    const float dfy = rcp ? __fmul_rn(gyn, __fdiv_rn(1.0f, sy)) : __fdiv_rn(gyn, sy);
-    gflow[(size_t)b * 2 * HW + rem] = __fmul_rn(dfx, 2.0f);
-    gflow[(size_t)b * 2 * HW + HW + rem] = __fmul_rn(dfy, 2.0f);
 }
 
 __device__ __forceinline__ void cswap(int &ka, float &wa, int &kb, float &wb) {
@@ -272,7 +313,7 @@ __device__ __forceinline__ void cswap(int &ka, float &wa, int &kb, float &wb) {
 
 template <int NS, typename T>
 __global__ void __launch_bounds__(kBlock)
-warp_gx_gather(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, int N, int C, int HW) {
+warp_gx_gather(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, int N, int C, int HW, FastDiv dHW) {
     constexpr int PPB = kBlock / NS;
     // slice 0 of every pixel loads and sorts the tap list once; the other slices read it from here
     __shared__ int s_src[NS > 1 ? kSlots : 1][NS > 1 ? PPB : 1];
@@ -286,12 +327,15 @@ warp_gx_gather(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, int
     int src[kSlots];
     float w[kSlots];
     if (cs == 0) {
+        // the first two entry pairs are requested together with the counter (no dependent round trip for the
+        // common case of <= 4 taps; slots past the counter hold stale bytes that are never used)
+        const int4 *e4 = reinterpret_cast<const int4 *>(ws.ent + (size_t)(live ? p : 0) * kSlots);
+        const int4 e01 = e4[0], e23 = e4[1];
         n = live ? min(ws.cnt[p], kSlots) : 0;
-        const int4 *e4 = reinterpret_cast<const int4 *>(ws.ent + (size_t)p * kSlots);
 #pragma unroll
         for (int i = 0; i < kSlots / 2; ++i) {
-            int4 e = make_int4(0, 0, 0, 0);
-            if (2 * i < n) e = e4[i];
+            int4 e = i == 0 ? e01 : (i == 1 ? e23 : make_int4(0, 0, 0, 0));
+            if (i >= 2 && 2 * i < n) e = e4[i];
             src[2 * i] = (2 * i < n) ? e.x : 0x7fffffff;
             w[2 * i] = (2 * i < n) ? __int_as_float(e.y) : 0.f;
             src[2 * i + 1] = (2 * i + 1 < n) ? e.z : 0x7fffffff;
@@ -328,12 +372,13 @@ warp_gx_gather(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, int
         }
     }
     if (!live) return;
-    const int b = p / HW, rem = p - b * HW;
+    const int b = dHW.div(p), rem = p - b * HW;
     const size_t step = (size_t)NS * HW;
     const T *plane = gout + ((size_t)b * C + cs) * HW;
     T *o = gx + ((size_t)b * C + cs) * HW + rem;
     // most targets receive <= 4 taps (exactly 4 for a smooth flow): the upper half is a rarely taken branch
-#pragma unroll 4
+    constexpr int UN = NS >= 4 ? 8 : 4;  // channels in flight per thread
+#pragma unroll UN
     for (int c = cs; c < C; c += NS, plane += step, o += step) {
         float acc = 0.f;
 #pragma unroll
@@ -402,7 +447,7 @@ static int warp_fwd_t(const T *x, const float *flow, T *out, int B, int C, int H
 #define USF_LAUNCH(NS)                                                                      \
     {                                                                                       \
         const int res = resident_ctas((const void *)warp_fwd_kernel<NS, T>);                \
-        warp_fwd_kernel<NS, T><<<blocks < res ? blocks : res, kBlock, 0, stream>>>(x, flow, out, N, C, H, W, border, rcp); \
+        warp_fwd_kernel<NS, T><<<blocks < res ? blocks : res, kBlock, 0, stream>>>(x, flow, out, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W)); \
     }
     switch (ns) {
         case 32: USF_LAUNCH(32); break;
@@ -419,8 +464,12 @@ static int warp_fwd_t(const T *x, const float *flow, T *out, int B, int C, int H
 template <int MODE, typename T>
 static cudaError_t launch_bwd(int ns, int blocks, const T *x, const float *flow, const T *gout, T *gx, float *gflow,
                               Workspace ws, int N, int C, int H, int W, int border, int rcp, cudaStream_t stream) {
-#define USF_LAUNCH(NS) \
-    warp_bwd_kernel<NS, MODE, T><<<blocks, kBlock, 0, stream>>>(x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp)
+#define USF_LAUNCH(NS)                                                                                          \
+    {                                                                                                           \
+        const int res = resident_ctas((const void *)warp_bwd_kernel<NS, MODE, T>);                              \
+        warp_bwd_kernel<NS, MODE, T><<<blocks < res ? blocks : res, kBlock, 0, stream>>>(                       \
+            x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W));       \
+    }
     switch (ns) {
         case 32: USF_LAUNCH(32); break;
         case 16: USF_LAUNCH(16); break;
@@ -456,7 +505,7 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
     if (e != cudaSuccess) { note_cuda_error(e); return USF_ERR_CUDA; }
     int st = note_launch(launch_bwd<1, T>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
     if (st != USF_OK) return st;
-#define USF_LAUNCH(NS) warp_gx_gather<NS, T><<<blocks, kBlock, 0, stream>>>(gout, gx, ws, N, C, HW)
+#define USF_LAUNCH(NS) warp_gx_gather<NS, T><<<blocks, kBlock, 0, stream>>>(gout, gx, ws, N, C, HW, make_fastdiv(HW))
     switch (ns) {
         case 32: USF_LAUNCH(32); break;
         case 16: USF_LAUNCH(16); break;
