@@ -377,8 +377,8 @@ warp_gx_gather(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, int
     const T *plane = gout + ((size_t)b * C + cs) * HW;
     T *o = gx + ((size_t)b * C + cs) * HW + rem;
     // most targets receive <= 4 taps (exactly 4 for a smooth flow): the upper half is a rarely taken branch
-    constexpr int UN = NS >= 4 ? 8 : 4;  // channels in flight per thread
-#pragma unroll UN
+    // (unroll 8 here costs registers and occupancy: measured 37 -> 46 us at 8x32x64x208)
+#pragma unroll 4
     for (int c = cs; c < C; c += NS, plane += step, o += step) {
         float acc = 0.f;
 #pragma unroll
