@@ -236,15 +236,17 @@ def test_warp_bwd_collapse_overflows_tap_lists(usf):
     pixels (far more than the 8 list slots each), exercising the overflow side list."""
     from oracle import c_oracle
     ops = usf.ops_mod
-    B, C, H, W = 1, 8, 16, 40
-    g = torch.Generator().manual_seed(11)
-    x, go = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
-    fl = torch.full((B, 2, H, W), 1000.0)
-    fl[:, :, : H // 2] = torch.randn(B, 2, H // 2, W, generator=g) * 0.3 + 5.5  # pile onto few targets
-    ogx, ogf = c_oracle.warp_bwd(x.numpy(), fl.numpy(), go.numpy(), "border")
-    gx, gf = ops.warp_bwd(x.cuda(), fl.cuda(), go.cuda(), "border")
-    check(gx, ogx, "gx with overflow")
-    check(gf, ogf, "gflow with overflow")
+    # 16x40: the fused small-image kernel (16 shared-memory slots + shared side list); 40x40 and 2 images: the
+    # three-kernel path (8 slots + global side list)
+    for B, C, H, W in [(1, 8, 16, 40), (2, 8, 40, 40), (2, 40, 10, 24)]:
+        g = torch.Generator().manual_seed(11)
+        x, go = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
+        fl = torch.full((B, 2, H, W), 1000.0)
+        fl[:, :, : H // 2] = torch.randn(B, 2, H // 2, W, generator=g) * 0.3 + 5.5  # pile onto few targets
+        ogx, ogf = c_oracle.warp_bwd(x.numpy(), fl.numpy(), go.numpy(), "border")
+        gx, gf = ops.warp_bwd(x.cuda(), fl.cuda(), go.cuda(), "border")
+        check(gx, ogx, f"gx with overflow {H}x{W}")
+        check(gf, ogf, f"gflow with overflow {H}x{W}")
 
 
 def test_warp_list_path_is_deterministic(usf):
@@ -259,6 +261,14 @@ def test_warp_list_path_is_deterministic(usf):
     # may differ between runs, and only in the last bits
     assert (a != b).float().mean().item() < 2e-2
     assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    # fused small-image kernel: lists of up to 16 taps are sorted -> bit-identical for a moderate flow
+    x = torch.randn(4, 96, 16, 52, generator=g).cuda()
+    go = torch.randn(4, 96, 16, 52, generator=g).cuda()
+    fl = (torch.randn(4, 2, 16, 52, generator=g) * 1.0).cuda()
+    a, fa = ops.warp_bwd(x, fl, go, "border")
+    for _ in range(5):
+        b, fb = ops.warp_bwd(x, fl, go, "border")
+        assert torch.equal(a, b) and torch.equal(fa, fb)
 
 
 # --------------------------------------------------------------------------------------------
@@ -412,17 +422,21 @@ def test_cuda_graph_capture_of_a_step(usf):
 
 def test_fallback_kernels_in_a_subprocess(usf):
     """USF_DISABLE_TMA=1 + USF_DIRECT_MAX_PIXELS=0 + USF_SMALL_MAX_HW=0 force the cp.async kernels that normally
-    only serve large odd-width shapes; USF_SMALL_MAX_HW=0 alone sends the tiny levels to the direct kernels.
+    only serve large odd-width shapes; USF_SMALL_MAX_HW=0 / USF_WARP_SMALL_MAX_HW=0 send the tiny levels to the direct corr kernels and the
+    three-kernel warp backward.
     Both must pass the same golden / oracle checks."""
     import os
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
     for extra in ({"USF_DISABLE_TMA": "1", "USF_DIRECT_MAX_PIXELS": "0", "USF_SMALL_MAX_HW": "0"},
-                  {"USF_SMALL_MAX_HW": "0"}):
+                  {"USF_SMALL_MAX_HW": "0", "USF_WARP_SMALL_MAX_HW": "0"}):
         env = dict(os.environ, **extra)
+        sel = "golden or corr_vs_oracle or nullable"
+        if "USF_WARP_SMALL_MAX_HW" in extra:  # small images through the three-kernel warp backward
+            sel += " or warp_vs_oracle or collapse"
         r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu",
-                            os.path.join(here, "test_gpu_parity.py"), "-k", "golden or corr_vs_oracle or nullable"],
+                            os.path.join(here, "test_gpu_parity.py"), "-k", sel],
                            env=env, capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, str(extra) + r.stdout[-3000:] + r.stderr[-2000:]
 

@@ -21,6 +21,8 @@
 //   warp_gx_overflow    targets hit by more than kSlots taps (e.g. a region clipped onto the image
 //                       border) keep their first kSlots taps in the list; the rest go through a
 //                       side list handled with float atomics after the gather has written g_x.
+#include <stdlib.h>
+
 #include <map>
 #include <mutex>
 #include <utility>
@@ -32,6 +34,7 @@ namespace {
 
 constexpr int kBlock = 256;
 constexpr int kSlots = 8;  // list capacity per target pixel
+constexpr int kSlotsS = 16;  // ... in the shared-memory lists of the fused small-image kernel
 
 // Division by a launch-time constant: q = floor(n / d) for 0 <= n < 2^31 as one IMAD.HI + add + shift
 // (M = ceil(2^(32+L) / d) = 2^32 + m with L = ceil(log2 d); the integer divides were a quarter of all
@@ -393,6 +396,178 @@ warp_gx_gather(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, int
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small images (H*W <= 1024: the coarse pyramid levels): the whole backward in ONE kernel, no workspace.
+// The three-kernel path above costs a memset node and three dependent launches (~15 us) for a few microseconds
+// of work there.  A CTA owns PPB target pixels of one image.  Every CTA rebuilds the image's taps (H*W
+// coordinate computations, cheap at this size) and keeps the ones that land on ITS targets in shared-memory
+// lists (shared-memory integer atomics for the slots, sorted by source afterwards: deterministic order);
+// taps beyond the 16 list slots go to a shared-memory side list that the target's own threads add before the
+// single plain store of each output -- no floating-point atomics at all, no zero-fill, no workspace.
+// ---------------------------------------------------------------------------------------------
+template <int NS, typename T>
+__global__ void __launch_bounds__(kBlock)
+warp_bwd_small(const T *__restrict__ x, const float *__restrict__ flow, const T *__restrict__ gout,
+               T *__restrict__ gx, float *__restrict__ gflow, int C, int H, int W, int border, int rcp,
+               FastDiv dW, FastDiv dBpi) {
+    constexpr int PPB = kBlock / NS;
+    extern __shared__ __align__(16) int sm_i[];
+    const int HW = H * W, cap = 4 * HW;
+    int *s_cnt = sm_i;                                            // [PPB] taps per target, [PPB] = overflow count
+    int *s_src = s_cnt + PPB + 4;                                 // [kSlotsS][PPB]
+    float *s_w = reinterpret_cast<float *>(s_src + kSlotsS * PPB); // [kSlotsS][PPB]
+    float *red = s_w + kSlotsS * PPB;                              // [2][NS][PPB]
+    int *o_tl = reinterpret_cast<int *>(red + 2 * kBlock);        // overflow: local target, source, weight
+    int *o_src = o_tl + cap;
+    float *o_w = reinterpret_cast<float *>(o_src + cap);
+    const int tid = threadIdx.x;
+    const int b = dBpi.div(blockIdx.x), t0 = (blockIdx.x - b * dBpi.d) * PPB;
+    const float *fl = flow + (size_t)b * 2 * HW;
+
+    for (int i = tid; i <= PPB; i += kBlock) s_cnt[i] = 0;
+    __syncthreads();
+    for (int src = tid; src < HW; src += kBlock) {
+        const int y = dW.div(src), xo = src - y * W;
+        const Taps t = make_taps(y, xo, __ldg(fl + src), __ldg(fl + HW + src), H, W, border, rcp);
+        const int off[4] = {t.o_nw, t.o_ne, t.o_sw, t.o_se};
+        const bool ok[4] = {t.k_nw, t.k_ne, t.k_sw, t.k_se};
+        const float wt[4] = {t.ex * t.ey, t.wx * t.ey, t.ex * t.wy, t.wx * t.wy};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int tl = off[k] - t0;
+            if (!ok[k] || wt[k] == 0.f || (unsigned)tl >= (unsigned)PPB) continue;
+            const int slot = atomicAdd(&s_cnt[tl], 1);
+            if (slot < kSlotsS) {
+                s_src[slot * PPB + tl] = src;
+                s_w[slot * PPB + tl] = wt[k];
+            } else {
+                const int j = atomicAdd(&s_cnt[PPB], 1);
+                o_tl[j] = tl;
+                o_src[j] = src;
+                o_w[j] = wt[k];
+            }
+        }
+    }
+    __syncthreads();
+
+    const int pl = tid % PPB, cs = tid / PPB;
+    const int rem = t0 + pl;
+    const bool live = rem < HW;
+    const size_t step = (size_t)NS * HW;
+    constexpr int UN = 4;
+    // g_flow partial sums of this thread's channel slice (same arithmetic as warp_bwd_kernel)
+    float gix = 0.f, giy = 0.f;
+    Taps t;
+    if (live && gflow != nullptr) {
+        const int y = dW.div(rem), xo = rem - y * W;
+        t = make_taps(y, xo, __ldg(fl + rem), __ldg(fl + HW + rem), H, W, border, rcp);
+        const T *gb = gout + ((size_t)b * C + cs) * HW + rem;
+        const T *p0 = x + ((size_t)b * C + cs) * HW + t.o_nw;
+        const T *p1 = p0 + W;
+#pragma unroll UN
+        for (int c = cs; c < C; c += NS, gb += step, p0 += step, p1 += step) {
+            const float go = ldf(gb);
+            const float vnw = t.k_nw ? ldf(p0) : 0.f, vne = t.k_ne ? ldf(p0 + 1) : 0.f;
+            const float vsw = t.k_sw ? ldf(p1) : 0.f, vse = t.k_se ? ldf(p1 + 1) : 0.f;
+            gix = fmaf(go, fmaf(t.ey, vne - vnw, t.wy * (vse - vsw)), gix);
+            giy = fmaf(go, fmaf(t.ex, vsw - vnw, t.wx * (vse - vne)), giy);
+        }
+    }
+    red[cs * PPB + pl] = gix;
+    red[kBlock + cs * PPB + pl] = giy;
+    // slice 0 sorts its target's list by source pixel (in place)
+    int n = min(s_cnt[pl], kSlotsS);
+    int src[kSlotsS];
+    float w[kSlotsS];
+    if (cs == 0) {
+#pragma unroll
+        for (int i = 0; i < kSlotsS; ++i) {
+            src[i] = i < n ? s_src[i * PPB + pl] : 0x7fffffff;
+            w[i] = i < n ? s_w[i * PPB + pl] : 0.f;
+        }
+        if (n <= 8) {
+#define USF_CS(a, b) cswap(src[a], w[a], src[b], w[b])
+            USF_CS(0, 1); USF_CS(2, 3); USF_CS(4, 5); USF_CS(6, 7);
+            USF_CS(0, 2); USF_CS(1, 3); USF_CS(4, 6); USF_CS(5, 7);
+            USF_CS(1, 2); USF_CS(5, 6); USF_CS(0, 4); USF_CS(3, 7);
+            USF_CS(1, 5); USF_CS(2, 6);
+            USF_CS(1, 4); USF_CS(3, 6);
+            USF_CS(2, 4); USF_CS(3, 5);
+            USF_CS(3, 4);
+#undef USF_CS
+        } else {
+            // Batcher odd-even merge sort, 16 keys, 63 comparators
+#define USF_CS(a, b) cswap(src[a], w[a], src[b], w[b])
+            USF_CS(0, 1); USF_CS(2, 3); USF_CS(4, 5); USF_CS(6, 7); USF_CS(8, 9); USF_CS(10, 11);
+            USF_CS(12, 13); USF_CS(14, 15); USF_CS(0, 2); USF_CS(1, 3); USF_CS(4, 6); USF_CS(5, 7);
+            USF_CS(8, 10); USF_CS(9, 11); USF_CS(12, 14); USF_CS(13, 15); USF_CS(1, 2); USF_CS(5, 6);
+            USF_CS(9, 10); USF_CS(13, 14); USF_CS(0, 4); USF_CS(1, 5); USF_CS(2, 6); USF_CS(3, 7);
+            USF_CS(8, 12); USF_CS(9, 13); USF_CS(10, 14); USF_CS(11, 15); USF_CS(2, 4); USF_CS(3, 5);
+            USF_CS(10, 12); USF_CS(11, 13); USF_CS(1, 2); USF_CS(3, 4); USF_CS(5, 6); USF_CS(9, 10);
+            USF_CS(11, 12); USF_CS(13, 14); USF_CS(0, 8); USF_CS(1, 9); USF_CS(2, 10); USF_CS(3, 11);
+            USF_CS(4, 12); USF_CS(5, 13); USF_CS(6, 14); USF_CS(7, 15); USF_CS(4, 8); USF_CS(5, 9);
+            USF_CS(6, 10); USF_CS(7, 11); USF_CS(2, 4); USF_CS(3, 5); USF_CS(6, 8); USF_CS(7, 9);
+            USF_CS(10, 12); USF_CS(11, 13); USF_CS(1, 2); USF_CS(3, 4); USF_CS(5, 6); USF_CS(7, 8);
+            USF_CS(9, 10); USF_CS(11, 12); USF_CS(13, 14);
+#undef USF_CS
+        }
+        if (NS > 1) {
+#pragma unroll
+            for (int i = 0; i < kSlotsS; ++i) {
+                s_src[i * PPB + pl] = src[i];
+                s_w[i * PPB + pl] = w[i];
+            }
+        }
+    }
+    __syncthreads();
+    if (!live) return;
+    if (gflow != nullptr && cs == 0) {
+        gix = red[pl];
+        giy = red[kBlock + pl];
+#pragma unroll
+        for (int s2 = 1; s2 < NS; ++s2) {
+            gix += red[s2 * PPB + pl];
+            giy += red[kBlock + s2 * PPB + pl];
+        }
+        const float sx = (float)(W - 1), sy = (float)(H - 1);
+        const float gxn = __fmul_rn(t.mx, gix), gyn = __fmul_rn(t.my, giy);
+        const float dfx = rcp ? __fmul_rn(gxn, __fdiv_rn(1.0f, sx)) : __fdiv_rn(gxn, sx);
+        const float dfy = rcp ? __fmul_rn(gyn, __fdiv_rn(1.0f, sy)) : __fdiv_rn(gyn, sy);
+        gflow[(size_t)b * 2 * HW + rem] = __fmul_rn(dfx, 2.0f);
+        gflow[(size_t)b * 2 * HW + HW + rem] = __fmul_rn(dfy, 2.0f);
+    }
+    if (cs != 0) {
+#pragma unroll
+        for (int i = 0; i < kSlotsS; ++i) {
+            src[i] = s_src[i * PPB + pl];
+            w[i] = s_w[i * PPB + pl];
+        }
+    }
+    const int novf = s_cnt[PPB];
+    const T *plane = gout + ((size_t)b * C + cs) * HW;
+    T *o = gx + ((size_t)b * C + cs) * HW + rem;
+#pragma unroll UN
+    for (int c = cs; c < C; c += NS, plane += step, o += step) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < n) acc = fmaf(w[i], ldf(plane + src[i]), acc);
+        if (n > 4) {
+#pragma unroll
+            for (int i = 4; i < 8; ++i)
+                if (i < n) acc = fmaf(w[i], ldf(plane + src[i]), acc);
+            if (n > 8) {
+#pragma unroll
+                for (int i = 8; i < kSlotsS; ++i)
+                    if (i < n) acc = fmaf(w[i], ldf(plane + src[i]), acc);
+            }
+        }
+        for (int j = 0; j < novf; ++j)  // rare: more than 16 taps on one target (flow collapsing onto a border)
+            if (o_tl[j] == pl) acc = fmaf(o_w[j], ldf(plane + o_src[j]), acc);
+        stf(o, acc);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBlock)
 warp_gx_overflow(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, int cap, int C, int HW) {
@@ -410,6 +585,13 @@ warp_gx_overflow(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, i
 // Channel slices per pixel: enough threads to fill the chip (~one full wave of 148 x 2048), but as few
 // slices as possible because every slice repeats the coordinate arithmetic (two IEEE divisions).  Small
 // levels end up with 4-8 channels per thread: their cost is the depth of the dependent-load chain.
+// images of at most this many pixels take the fused single-kernel backward (USF_WARP_SMALL_MAX_HW=0 disables)
+const int kWarpSmallMaxHW = [] {
+    const char *e = getenv("USF_WARP_SMALL_MAX_HW");
+    const int v = e ? atoi(e) : 1024;
+    return v > 1024 ? 1024 : v;
+}();
+
 int pick_ns(int C, int N) {
     int ns = 1;
     const long wave = 148L * 2048;
@@ -500,6 +682,25 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
     }
     if (workspace == nullptr || workspace_bytes < ws_bytes((size_t)N) || ((uintptr_t)workspace & 15))
         return USF_ERR_WORKSPACE;
+    if (HW <= kWarpSmallMaxHW) {  // one fused kernel, workspace untouched
+        const int ppb = kBlock / ns, bpi = (HW + ppb - 1) / ppb;
+        const size_t smem = ((size_t)(ppb + 4) + 2 * kSlotsS * ppb + 2 * kBlock + 3 * 4 * HW) * 4;
+        cudaError_t e = cudaSuccess;
+#define USF_LAUNCH(NS)                                                                                       \
+    if ((e = ensure_smem((const void *)warp_bwd_small<NS, T>, (int)smem)) == cudaSuccess)                    \
+        warp_bwd_small<NS, T><<<B * bpi, kBlock, smem, stream>>>(x, flow, gout, gx, gflow, C, H, W, border, rcp, \
+                                                                 make_fastdiv(W), make_fastdiv(bpi));
+        switch (ns) {
+            case 32: USF_LAUNCH(32); break;
+            case 16: USF_LAUNCH(16); break;
+            case 8: USF_LAUNCH(8); break;
+            case 4: USF_LAUNCH(4); break;
+            case 2: USF_LAUNCH(2); break;
+            default: USF_LAUNCH(1); break;
+        }
+#undef USF_LAUNCH
+        return note_launch(e != cudaSuccess ? e : cudaGetLastError());
+    }
     ws = carve(workspace, (size_t)N);
     cudaError_t e = cudaMemsetAsync(ws.cnt, 0, cnt_bytes((size_t)N) + 16, stream);
     if (e != cudaSuccess) { note_cuda_error(e); return USF_ERR_CUDA; }
