@@ -198,13 +198,15 @@ corr_bwd_gather(const float *__restrict__ xin, const float *__restrict__ gout, f
 // ===========================================================================================
 constexpr int NCW = CG / CT;                                 // 4 consumer warps
 constexpr int T_THREADS = 32 * (NCW + 1);                    // + 1 producer warp
-constexpr int XW_BYTES = CT * XR * XS * 4;                   // 22528: one warp's 8-channel halo box
 constexpr int NBAR = NCW + 4;                                // xfull[4], gfull[2], gempty[2]
 
-template <bool GX2> struct GTile {
+// CTT = channels per thread: 8 (CTA = 32 channels, 2 CTAs/SM) when the grid fills the chip, 4 (CTA = 16
+// channels, 3 CTAs/SM, twice the CTAs, half the dependent work per warp) when it would not.
+template <bool GX2, int CTT = CT> struct GTile {
     static constexpr int kStride = GX2 ? XS : GS;            // 44 (halo box) : 36
     static constexpr int kBytes = kD * TH * kStride * 4;     // 12672 : 10368
-    static constexpr int kSmem = NCW * XW_BYTES + 2 * kBytes + NBAR * 8;  // barriers live at the end
+    static constexpr int kXW = CTT * XR * XS * 4;            // one warp's halo box: 22528 (8 ch) / 11264 (4 ch)
+    static constexpr int kSmem = NCW * kXW + 2 * kBytes + NBAR * 8;  // barriers live at the end
 };
 
 // eight G values of displacement dxi for this thread's pixels (row base pointer `row`)
@@ -244,11 +246,14 @@ struct GLoader<GX2, kD> {
 
 // mx: box [8ch][16][44] over the feature map.  mg over gout: gx1 box [9ch][8][36], gx2 box [9ch][8][44].
 // grid = (tiles_x, tiles_y, B * ngroups)
-template <bool GX2>
+template <bool GX2, int CTT>
 __device__ __forceinline__ void bwd_tile(unsigned char *smem_raw, const CUtensorMap &mx, const CUtensorMap &mg,
                                          float *__restrict__ gx, int C, int H, int W, int ngroups, int zidx,
                                          float rc) {
-    constexpr int GB = GTile<GX2>::kBytes;
+    constexpr int GB = GTile<GX2, CTT>::kBytes;
+    constexpr int XW_BYTES = GTile<GX2, CTT>::kXW;
+    constexpr int CG = NCW * CTT;  // channels per CTA (shadows the 32 of the cp.async kernels)
+    constexpr int CT = CTT;
     unsigned char *gbase = smem_raw + NCW * XW_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(gbase + 2 * GB);
     uint64_t *xfull = bars, *gfull = bars + NCW, *gempty = bars + NCW + 2;
@@ -351,7 +356,8 @@ __device__ __forceinline__ void bwd_tile(unsigned char *smem_raw, const CUtensor
 // gx1 and gx2 halves of the grid are independent, so the fused grid packs the SMs better than two
 // back-to-back launches (twice the CTAs per wave tail) and saves a launch.
 // z layout: [0, nz) -> first requested gradient, [nz, 2 nz) -> gx2 when both are requested.
-__global__ void __launch_bounds__(T_THREADS, 2)
+template <int CTT>
+__global__ void __launch_bounds__(T_THREADS, CTT == 8 ? 2 : 3)
 corr_bwd_gather_tma(const __grid_constant__ CUtensorMap mx1, const __grid_constant__ CUtensorMap mg1,
                     const __grid_constant__ CUtensorMap mx2, const __grid_constant__ CUtensorMap mg2,
                     float *__restrict__ gx1, float *__restrict__ gx2, int C, int H, int W, int ngroups, int nz,
@@ -361,22 +367,30 @@ corr_bwd_gather_tma(const __grid_constant__ CUtensorMap mx1, const __grid_consta
     const bool second = (gx1 == nullptr) || z >= nz;
     if (z >= nz) z -= nz;
     if (second)
-        bwd_tile<true>(smem_raw, mx2, mg2, gx2, C, H, W, ngroups, z, rc);
+        bwd_tile<true, CTT>(smem_raw, mx2, mg2, gx2, C, H, W, ngroups, z, rc);
     else
-        bwd_tile<false>(smem_raw, mx1, mg1, gx1, C, H, W, ngroups, z, rc);
+        bwd_tile<false, CTT>(smem_raw, mx1, mg1, gx1, C, H, W, ngroups, z, rc);
 }
 
+template <int CTT>
 cudaError_t launch_tma(const CUtensorMap &mx1, const CUtensorMap &mg1, const CUtensorMap &mx2,
                        const CUtensorMap &mg2, float *gx1, float *gx2, int B, int C, int H, int W,
                        cudaStream_t stream) {
-    constexpr int SM = GTile<true>::kSmem > GTile<false>::kSmem ? GTile<true>::kSmem : GTile<false>::kSmem;
-    if (cudaError_t once = ensure_smem((const void *)corr_bwd_gather_tma, SM)) return once;
-    const int ngroups = (C + CG - 1) / CG;
+    constexpr int SM = GTile<true, CTT>::kSmem > GTile<false, CTT>::kSmem ? GTile<true, CTT>::kSmem
+                                                                          : GTile<false, CTT>::kSmem;
+    if (cudaError_t once = ensure_smem((const void *)corr_bwd_gather_tma<CTT>, SM)) return once;
+    const int ngroups = (C + NCW * CTT - 1) / (NCW * CTT);
     const int nz = B * ngroups;
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, nz * ((gx1 && gx2) ? 2 : 1));
-    corr_bwd_gather_tma<<<grid, T_THREADS, SM, stream>>>(mx1, mg1, mx2, mg2, gx1, gx2, C, H, W, ngroups, nz,
-                                                         1.0f / (float)C);
+    corr_bwd_gather_tma<CTT><<<grid, T_THREADS, SM, stream>>>(mx1, mg1, mx2, mg2, gx1, gx2, C, H, W, ngroups, nz,
+                                                              1.0f / (float)C);
     return cudaGetLastError();
+}
+
+// CTAs of the 8-channel-per-thread configuration; below ~3/4 of a wave (2 CTAs/SM) the 4-channel one is used
+inline bool thin_grid(int B, int C, int H, int W, int ngrad) {
+    const long ctas = (long)((W + TW - 1) / TW) * ((H + TH - 1) / TH) * B * ((C + CG - 1) / CG) * ngrad;
+    return ctas * 4 < 148L * 2 * 3;
 }
 
 template <bool GX2, bool VEC>
@@ -406,12 +420,15 @@ int corr_bwd_f32(const float *x1, const float *x2, const float *gout, float *gx1
         // TMA path (tensor maps encoded per call, passed as __grid_constant__ parameters)
         CUtensorMap mx1 = {}, mg1 = {}, mx2 = {}, mg2 = {};
         bool ok = true;
-        if (gx1) ok = make_nchw_map(&mx1, x2, B, C, H, W, XS, XR, CT) && make_nchw_map(&mg1, gout, B, kK, H, W, GS, TH, kD);
-        if (ok && gx2) ok = make_nchw_map(&mx2, x1, B, C, H, W, XS, XR, CT) && make_nchw_map(&mg2, gout, B, kK, H, W, XS, TH, kD);
+        const bool thin = thin_grid(B, C, H, W, (gx1 && gx2) ? 2 : 1);
+        const int ctt = thin ? 4 : CT;
+        if (gx1) ok = make_nchw_map(&mx1, x2, B, C, H, W, XS, XR, ctt) && make_nchw_map(&mg1, gout, B, kK, H, W, GS, TH, kD);
+        if (ok && gx2) ok = make_nchw_map(&mx2, x1, B, C, H, W, XS, XR, ctt) && make_nchw_map(&mg2, gout, B, kK, H, W, XS, TH, kD);
         if (ok) {
             if (!gx1) { mx1 = mx2; mg1 = mg2; }
             if (!gx2) { mx2 = mx1; mg2 = mg1; }
-            return note_launch(launch_tma(mx1, mg1, mx2, mg2, gx1, gx2, B, C, H, W, stream));
+            return note_launch(thin ? launch_tma<4>(mx1, mg1, mx2, mg2, gx1, gx2, B, C, H, W, stream)
+                                    : launch_tma<8>(mx1, mg1, mx2, mg2, gx1, gx2, B, C, H, W, stream));
         }
         // encoding failed (driver entry point missing / TMA disabled): fall through to the cp.async kernels
     }
