@@ -19,6 +19,8 @@
 // tile as four 8-channel boxes, the G stage as one 9-channel box (see the TMA section below for how
 // the shifted G tile of gx2 is handled).  One producer lane feeds 4 consumer warps through
 // full/empty mbarriers (no __syncthreads in the loop).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -249,7 +251,7 @@ struct GLoader<GX2, kD> {
 template <bool GX2, int CTT>
 __device__ __forceinline__ void bwd_tile(unsigned char *smem_raw, const CUtensorMap &mx, const CUtensorMap &mg,
                                          float *__restrict__ gx, int C, int H, int W, int ngroups, int zidx,
-                                         float rc) {
+                                         int tx, int ty, float rc) {
     constexpr int GB = GTile<GX2, CTT>::kBytes;
     constexpr int XW_BYTES = GTile<GX2, CTT>::kXW;
     constexpr int CG = NCW * CTT;  // channels per CTA (shadows the 32 of the cp.async kernels)
@@ -258,7 +260,7 @@ __device__ __forceinline__ void bwd_tile(unsigned char *smem_raw, const CUtensor
     uint64_t *bars = reinterpret_cast<uint64_t *>(gbase + 2 * GB);
     uint64_t *xfull = bars, *gfull = bars + NCW, *gempty = bars + NCW + 2;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int x0 = tx * TW, y0 = ty * TH;
     const int b = zidx / ngroups, cg = zidx - b * ngroups;
     const int c0 = cg * CG;
     if (tid == 0) {
@@ -367,9 +369,144 @@ corr_bwd_gather_tma(const __grid_constant__ CUtensorMap mx1, const __grid_consta
     const bool second = (gx1 == nullptr) || z >= nz;
     if (z >= nz) z -= nz;
     if (second)
-        bwd_tile<true, CTT>(smem_raw, mx2, mg2, gx2, C, H, W, ngroups, z, rc);
+        bwd_tile<true, CTT>(smem_raw, mx2, mg2, gx2, C, H, W, ngroups, z, blockIdx.x, blockIdx.y, rc);
     else
-        bwd_tile<false, CTT>(smem_raw, mx1, mg1, gx1, C, H, W, ngroups, z, rc);
+        bwd_tile<false, CTT>(smem_raw, mx1, mg1, gx1, C, H, W, ngroups, z, blockIdx.x, blockIdx.y, rc);
+}
+
+// -------------------------------------------------------------------------------------------
+// 16x16 tile geometry for gx1.  Widths like 208 = 6.5 x 32 leave the last 8x32 tile column half empty; at
+// 8x32x64x208 that made 896 CTAs = 3.03 waves of the 296 resident ones, i.e. a fourth round for 8 CTAs.
+// 16x16 tiles cover such a level exactly.  Same thread tile (8 pixels x 8 channels), lanes mapped as
+// (row = lane & 15, strip = lane >> 4) so that a quarter-warp reads 8 different rows: strides of 7 (X halo,
+// 24x28) and 5 (G tile, 16x20) 16-byte chunks are conflict-free.  Only gx1 can take it: the gx2 halo stage
+// would need 2 x 16 KB more than two CTAs per SM allow, so a mixed launch runs gx1 on 16x16 and gx2 on 8x32
+// tiles (864 CTAs, 3 rounds).
+// -------------------------------------------------------------------------------------------
+constexpr int SQ = 16;                        // tile edge
+constexpr int XR2 = SQ + 2 * kMaxDisp;        // 24 halo rows
+constexpr int XS2 = 28;                       // halo row stride (24 columns used)
+constexpr int GS2 = 20;                       // G tile row stride (16 columns used)
+constexpr int XW2_BYTES = CT * XR2 * XS2 * 4; // 21504
+constexpr int G2_BYTES = kD * SQ * GS2 * 4;   // 11520
+constexpr int SQ_SMEM = NCW * XW2_BYTES + 2 * G2_BYTES + NBAR * 8;
+
+__device__ __forceinline__ void bwd_tile_sq(unsigned char *smem_raw, const CUtensorMap &mx, const CUtensorMap &mg,
+                                            float *__restrict__ gx, int C, int H, int W, int ngroups, int zidx,
+                                            int tx, int ty, float rc) {
+    unsigned char *gbase = smem_raw + NCW * XW2_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(gbase + 2 * G2_BYTES);
+    uint64_t *xfull = bars, *gfull = bars + NCW, *gempty = bars + NCW + 2;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int x0 = tx * SQ, y0 = ty * SQ;
+    const int b = zidx / ngroups, cg = zidx - b * ngroups;
+    const int c0 = cg * CG;
+    if (tid == 0) {
+#pragma unroll
+        for (int w = 0; w < NCW; ++w) mbar_init(&xfull[w], 1);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&gfull[s], 1);
+            mbar_init(&gempty[s], NCW);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == NCW) {
+        if (lane == 0) {
+            tma_prefetch_desc(&mx);
+            tma_prefetch_desc(&mg);
+#pragma unroll 1
+            for (int dyi = 0; dyi < kD; ++dyi) {
+                const int s = dyi & 1;
+                if (dyi >= 2) mbar_wait(&gempty[s], ((dyi >> 1) - 1) & 1);
+                mbar_expect_tx(&gfull[s], G2_BYTES);
+                tma_load_4d(gbase + s * G2_BYTES, &mg, &gfull[s], x0, y0, dyi * kD, b);
+                if (dyi == 0) {
+#pragma unroll 1
+                    for (int w = 0; w < NCW; ++w) {
+                        mbar_expect_tx(&xfull[w], XW2_BYTES);
+                        tma_load_4d(smem_raw + w * XW2_BYTES, &mx, &xfull[w], x0 - kMaxDisp, y0 - kMaxDisp,
+                                    c0 + w * CT, b);
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    const int r = lane & 15, q = lane >> 4;
+    float acc[CT][8];
+#pragma unroll
+    for (int c = 0; c < CT; ++c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[c][i] = 0.f;
+
+    const float *xw = reinterpret_cast<const float *>(smem_raw + warp * XW2_BYTES) + r * XS2 + 8 * q;
+    mbar_wait(&xfull[warp], 0);
+#pragma unroll 1
+    for (int dyi = 0; dyi < kD; ++dyi) {
+        const int s = dyi & 1;
+        mbar_wait(&gfull[s], (dyi >> 1) & 1);
+        const float *gs = reinterpret_cast<const float *>(gbase + s * G2_BYTES) + r * GS2 + 8 * q;
+        float g[kD][8];
+#pragma unroll
+        for (int dx = 0; dx < kD; ++dx) {
+            const float4 g0 = lds128(gs + dx * SQ * GS2), g1 = lds128(gs + dx * SQ * GS2 + 4);
+            g[dx][0] = g0.x; g[dx][1] = g0.y; g[dx][2] = g0.z; g[dx][3] = g0.w;
+            g[dx][4] = g1.x; g[dx][5] = g1.y; g[dx][6] = g1.z; g[dx][7] = g1.w;
+        }
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const float *p = xw + (c * XR2 + dyi) * XS2;
+            const float4 w0 = lds128(p), w1 = lds128(p + 4), w2 = lds128(p + 8), w3 = lds128(p + 12);
+            const float w[16] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w,
+                                 w2.x, w2.y, w2.z, w2.w, w3.x, w3.y, w3.z, w3.w};
+#pragma unroll
+            for (int dx = 0; dx < kD; ++dx)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(g[dx][i], w[dx + i], acc[c][i]);
+            if (c == 0) {  // release the G stage only after its values have been consumed (see bwd_tile)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&gempty[s]);
+            }
+        }
+    }
+
+    const int gy = y0 + r, gxx = x0 + 8 * q;
+    if (gy >= H) return;
+#pragma unroll
+    for (int c = 0; c < CT; ++c) {
+        const int cc = c0 + warp * CT + c;
+        if (cc >= C) break;
+        float *o = gx + (((size_t)b * C + cc) * H + gy) * W + gxx;
+        if (gxx < W)
+            *reinterpret_cast<float4 *>(o) =
+                make_float4(acc[c][0] * rc, acc[c][1] * rc, acc[c][2] * rc, acc[c][3] * rc);
+        if (gxx + 4 < W)
+            *reinterpret_cast<float4 *>(o + 4) =
+                make_float4(acc[c][4] * rc, acc[c][5] * rc, acc[c][6] * rc, acc[c][7] * rc);
+    }
+}
+
+// mixed launch, 1-D grid: CTAs [0, n2) compute gx2 on 8x32 tiles, the rest gx1 on 16x16 tiles
+__global__ void __launch_bounds__(T_THREADS, 2)
+corr_bwd_gather_tma_mixed(const __grid_constant__ CUtensorMap mx1, const __grid_constant__ CUtensorMap mg1,
+                          const __grid_constant__ CUtensorMap mx2, const __grid_constant__ CUtensorMap mg2,
+                          float *__restrict__ gx1, float *__restrict__ gx2, int C, int H, int W, int ngroups, int nz,
+                          int t32x, int t32y, int t16x, int t16y, float rc) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    int id = blockIdx.x;
+    const int n2 = t32x * t32y * nz;
+    if (id < n2) {
+        const int tx = id % t32x, ty = (id / t32x) % t32y, z = id / (t32x * t32y);
+        bwd_tile<true, CT>(smem_raw, mx2, mg2, gx2, C, H, W, ngroups, z, tx, ty, rc);
+    } else {
+        id -= n2;
+        const int tx = id % t16x, ty = (id / t16x) % t16y, z = id / (t16x * t16y);
+        bwd_tile_sq(smem_raw, mx1, mg1, gx1, C, H, W, ngroups, z, tx, ty, rc);
+    }
 }
 
 template <int CTT>
@@ -385,6 +522,15 @@ cudaError_t launch_tma(const CUtensorMap &mx1, const CUtensorMap &mg1, const CUt
     corr_bwd_gather_tma<CTT><<<grid, T_THREADS, SM, stream>>>(mx1, mg1, mx2, mg2, gx1, gx2, C, H, W, ngroups, nz,
                                                               1.0f / (float)C);
     return cudaGetLastError();
+}
+
+// USF_BWD_MIXED_TILES=0 keeps both gradients on 8x32 tiles (A/B runs, fallback tests)
+inline bool mixed_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("USF_BWD_MIXED_TILES");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 
 // CTAs of the 8-channel-per-thread configuration; below ~3/4 of a wave (2 CTAs/SM) the 4-channel one is used
@@ -421,6 +567,22 @@ int corr_bwd_f32(const float *x1, const float *x2, const float *gout, float *gx1
         CUtensorMap mx1 = {}, mg1 = {}, mx2 = {}, mg2 = {};
         bool ok = true;
         const bool thin = thin_grid(B, C, H, W, (gx1 && gx2) ? 2 : 1);
+        if (!thin && gx1 && gx2 && mixed_enabled()) {
+            // gx1 on 16x16 tiles when that saves a round of resident CTAs (2 per SM)
+            const int ngroups = (C + CG - 1) / CG, nz = B * ngroups;
+            const int t32x = (W + TW - 1) / TW, t32y = (H + TH - 1) / TH;
+            const int t16x = (W + SQ - 1) / SQ, t16y = (H + SQ - 1) / SQ;
+            const long slots = 148L * 2, now = 2L * t32x * t32y * nz, mix = (long)(t32x * t32y + t16x * t16y) * nz;
+            if ((mix + slots - 1) / slots < (now + slots - 1) / slots &&
+                make_nchw_map(&mx1, x2, B, C, H, W, XS2, XR2, CT) && make_nchw_map(&mg1, gout, B, kK, H, W, GS2, SQ, kD) &&
+                make_nchw_map(&mx2, x1, B, C, H, W, XS, XR, CT) && make_nchw_map(&mg2, gout, B, kK, H, W, XS, TH, kD)) {
+                constexpr int SM = GTile<true, CT>::kSmem > SQ_SMEM ? GTile<true, CT>::kSmem : SQ_SMEM;
+                if (cudaError_t once = ensure_smem((const void *)corr_bwd_gather_tma_mixed, SM)) return note_launch(once);
+                corr_bwd_gather_tma_mixed<<<(unsigned)mix, T_THREADS, SM, stream>>>(
+                    mx1, mg1, mx2, mg2, gx1, gx2, C, H, W, ngroups, nz, t32x, t32y, t16x, t16y, 1.0f / (float)C);
+                return note_launch(cudaGetLastError());
+            }
+        }
         const int ctt = thin ? 4 : CT;
         if (gx1) ok = make_nchw_map(&mx1, x2, B, C, H, W, XS, XR, ctt) && make_nchw_map(&mg1, gout, B, kK, H, W, GS, TH, kD);
         if (ok && gx2) ok = make_nchw_map(&mx2, x1, B, C, H, W, XS, XR, ctt) && make_nchw_map(&mg2, gout, B, kK, H, W, XS, TH, kD);
