@@ -94,7 +94,10 @@ int usf_corr_fwd(const void *x1, const void *x2, void *out, int B, int C, int H,
 /*
  * Gradients of the cost volume.  gout: [B,81,H,W].  gx1 / gx2: [B,C,H,W], either
  * may be NULL (not needed).  Both are computed as gathers: no atomics, outputs
- * fully overwritten.
+ * fully overwritten, bit-identical from run to run.  (Images of <= 256 pixels are
+ * processed packed in shared memory; there a NON-FINITE feature value in a column
+ * next to the image border can reach a border gradient as 0 * inf.  Finite inputs
+ * are exact.)
  */
 int usf_corr_bwd(const void *x1, const void *x2, const void *gout, void *gx1, void *gx2, int B,
                  int C, int H, int W, int max_disp, int dtype, unsigned flags, void *stream);
@@ -108,9 +111,11 @@ int usf_corr_bwd(const void *x1, const void *x2, const void *gout, void *gx1, vo
 int usf_warp_fwd(const void *x, const float *flow, void *out, int B, int C, int H, int W,
                  int pad_mode, int dtype, unsigned flags, void *stream);
 
-/* Bytes of scratch usf_warp_bwd needs when gx != NULL (0 when only gflow is wanted
- * or USF_FLAG_WARP_BWD_ATOMIC is set).  Contents need no initialisation; the pointer passed
- * to usf_warp_bwd must be 16-byte aligned. */
+/* Bytes of scratch usf_warp_bwd needs when gx != NULL (0 when only gflow is wanted,
+ * USF_FLAG_WARP_BWD_ATOMIC is set, or the image is small enough -- H*W <= 1024 -- for
+ * the single-kernel path, which keeps its tap lists in shared memory; workspace may
+ * then be NULL).  Contents need no initialisation; the pointer passed to usf_warp_bwd
+ * must be 16-byte aligned. */
 size_t usf_warp_bwd_workspace_bytes(int B, int C, int H, int W, unsigned flags);
 
 /*

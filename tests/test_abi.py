@@ -58,13 +58,17 @@ def test_argument_validation_without_a_gpu(lib):
     assert lib.usf_warp_fwd(p, p, p, 1, 1, 2, 2, 5, 0, 0, None) == BAD_ARG
     assert lib.usf_warp_fwd(p, p, p, 1, 1, 1, 2, 0, 0, 0, None) == BAD_SHAPE
     assert lib.usf_warp_bwd(p, p, p, None, None, 1, 1, 2, 2, 0, 0, 0, None, 0, None) == 0
-    assert lib.usf_warp_bwd(p, p, p, p, p, 1, 1, 2, 2, 0, 0, 0, None, 0, None) == WORKSPACE
-    need = lib.usf_warp_bwd_workspace_bytes(1, 1, 2, 2, 0)
+    # images above 1024 pixels take the three-kernel path, which needs the caller's workspace
+    assert lib.usf_warp_bwd(p, p, p, p, p, 1, 1, 40, 40, 0, 0, 0, None, 0, None) == WORKSPACE
+    need = lib.usf_warp_bwd_workspace_bytes(1, 1, 40, 40, 0)
     assert need > 0
-    assert lib.usf_warp_bwd(p, p, p, p, p, 1, 1, 2, 2, 0, 0, 0, p, need - 1, None) == WORKSPACE
-    assert lib.usf_warp_bwd_workspace_bytes(1, 1, 2, 2, 4) == 0  # atomic mode needs none
+    assert lib.usf_warp_bwd(p, p, p, p, p, 1, 1, 40, 40, 0, 0, 0, p, need - 1, None) == WORKSPACE
+    assert lib.usf_warp_bwd_workspace_bytes(1, 1, 40, 40, 4) == 0  # atomic mode needs none
     assert lib.usf_warp_bwd_workspace_bytes(8, 32, 64, 208, 0) == 8 * 64 * 208 * (4 + 64 + 48) + 16
-    assert lib.usf_warp_bwd_workspace_bytes(1, 1, 3, 3, 0) == 48 + 16 + 9 * (64 + 48)  # cnt padded to 16 B
+    assert lib.usf_warp_bwd_workspace_bytes(1, 1, 33, 33, 0) == 4368 + 16 + 1089 * (64 + 48)  # cnt padded to 16 B
+    # ... smaller ones run as one kernel with shared-memory tap lists: no workspace
+    assert lib.usf_warp_bwd_workspace_bytes(8, 96, 16, 52, 0) == 0
+    assert lib.usf_warp_bwd_workspace_bytes(1, 1, 32, 32, 0) == 0
 
 
 def test_launch_counter_is_per_thread_and_resettable(lib):

@@ -16,7 +16,7 @@ int corr_bwd_f32(const float *, const float *, const float *, float *, float *, 
 int warp_fwd_f32(const float *, const float *, float *, int, int, int, int, int, unsigned, cudaStream_t);
 int warp_bwd_f32(const float *, const float *, const float *, float *, float *, int, int, int, int, int,
                  unsigned, void *, size_t, cudaStream_t);
-size_t warp_bwd_workspace_bytes(size_t N);
+size_t warp_bwd_workspace_bytes(int B, int H, int W);
 int corr_fwd_bf16(const void *, const void *, void *, int, int, int, int, unsigned, float, cudaStream_t);
 int corr_fwd_bf16_tiled(const void *, const void *, void *, int, int, int, int, unsigned, float, cudaStream_t);
 int corr_bwd_bf16(const void *, const void *, const void *, void *, void *, int, int, int, int, cudaStream_t);
@@ -163,7 +163,7 @@ int usf_warp_fwd(const void *x, const float *flow, void *out, int B, int C, int 
 size_t usf_warp_bwd_workspace_bytes(int B, int C, int H, int W, unsigned flags) {
     (void)C;
     if (B <= 0 || H <= 0 || W <= 0 || (flags & USF_FLAG_WARP_BWD_ATOMIC)) return 0;
-    return warp_bwd_workspace_bytes((size_t)B * H * W);
+    return warp_bwd_workspace_bytes(B, H, W);
 }
 
 int usf_warp_bwd(const void *x, const float *flow, const void *gout, void *gx, float *gflow, int B, int C,

@@ -601,7 +601,10 @@ int pick_ns(int C, int N) {
 
 }  // namespace
 
-size_t warp_bwd_workspace_bytes(size_t N) { return ws_bytes(N); }
+// images handled by the fused kernel need no workspace
+size_t warp_bwd_workspace_bytes(int B, int H, int W) {
+    return (long)H * W <= kWarpSmallMaxHW ? 0 : ws_bytes((size_t)B * H * W);
+}
 
 // CTAs of `kernel` that fit on the device at once (cached per kernel and device)
 static int resident_ctas(const void *kernel) {
@@ -680,9 +683,7 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
         if (e != cudaSuccess) { note_cuda_error(e); return USF_ERR_CUDA; }
         return note_launch(launch_bwd<2, T>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
     }
-    if (workspace == nullptr || workspace_bytes < ws_bytes((size_t)N) || ((uintptr_t)workspace & 15))
-        return USF_ERR_WORKSPACE;
-    if (HW <= kWarpSmallMaxHW) {  // one fused kernel, workspace untouched
+    if (HW <= kWarpSmallMaxHW) {  // one fused kernel, no workspace
         const int ppb = kBlock / ns, bpi = (HW + ppb - 1) / ppb;
         const size_t smem = ((size_t)(ppb + 4) + 2 * kSlotsS * ppb + 2 * kBlock + 3 * 4 * HW) * 4;
         cudaError_t e = cudaSuccess;
@@ -701,6 +702,8 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
 #undef USF_LAUNCH
         return note_launch(e != cudaSuccess ? e : cudaGetLastError());
     }
+    if (workspace == nullptr || workspace_bytes < ws_bytes((size_t)N) || ((uintptr_t)workspace & 15))
+        return USF_ERR_WORKSPACE;
     ws = carve(workspace, (size_t)N);
     cudaError_t e = cudaMemsetAsync(ws.cnt, 0, cnt_bytes((size_t)N) + 16, stream);
     if (e != cudaSuccess) { note_cuda_error(e); return USF_ERR_CUDA; }
