@@ -476,7 +476,8 @@ def check_bf16(got, want, what):
 
 
 @pytest.mark.parametrize("shape", [(2, 64, 8, 26), (1, 33, 5, 11), (2, 32, 32, 104), (1, 96, 16, 52),
-                                   (8, 32, 64, 208), (2, 64, 48, 104), (1, 196, 24, 40), (3, 20, 9, 72)],
+                                   (8, 32, 64, 208), (2, 64, 48, 104), (1, 196, 24, 40), (3, 20, 9, 72),
+                                   (8, 196, 24, 40), (8, 20, 9, 72), (2, 40, 30, 88)],
                          ids=lambda s: "x".join(map(str, s)))
 def test_bf16_corr_vs_oracle(usf, shape):
     from oracle import c_oracle
@@ -493,6 +494,10 @@ def test_bf16_corr_vs_oracle(usf, shape):
     o1, o2 = c_oracle.corr_bwd(x1.float().numpy(), x2.float().numpy(), go.float().numpy())
     check_bf16(g1, o1, "gx1")
     check_bf16(g2, o2, "gx2")
+    only1, none = ops.corr_bwd(x1.cuda(), x2.cuda(), go.cuda(), need_gx2=False)
+    assert none is None and torch.equal(only1, g1)
+    none, only2 = ops.corr_bwd(x1.cuda(), x2.cuda(), go.cuda(), need_gx1=False)
+    assert none is None and torch.equal(only2, g2)
 
 
 @pytest.mark.parametrize("pad", ["border", "zeros"])

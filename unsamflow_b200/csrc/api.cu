@@ -20,6 +20,7 @@ size_t warp_bwd_workspace_bytes(int B, int H, int W);
 int corr_fwd_bf16(const void *, const void *, void *, int, int, int, int, unsigned, float, cudaStream_t);
 int corr_fwd_bf16_tiled(const void *, const void *, void *, int, int, int, int, unsigned, float, cudaStream_t);
 int corr_bwd_bf16(const void *, const void *, const void *, void *, void *, int, int, int, int, cudaStream_t);
+int corr_bwd_bf16_tiled(const void *, const void *, const void *, void *, void *, int, int, int, int, cudaStream_t);
 int warp_fwd_bf16(const void *, const float *, void *, int, int, int, int, int, unsigned, cudaStream_t);
 int warp_bwd_bf16(const void *, const float *, const void *, void *, float *, int, int, int, int, int, unsigned,
                   void *, size_t, cudaStream_t);
@@ -142,7 +143,13 @@ int usf_corr_bwd(const void *x1, const void *x2, const void *gout, void *gx1, vo
     if (dtype == USF_F32)
         return corr_bwd_f32((const float *)x1, (const float *)x2, (const float *)gout, (float *)gx1,
                             (float *)gx2, B, C, H, W, (cudaStream_t)stream);
-    if (dtype == USF_BF16) return corr_bwd_bf16(x1, x2, gout, gx1, gx2, B, C, H, W, (cudaStream_t)stream);
+    if (dtype == USF_BF16) {
+        if ((long)B * H * W > kDirectMaxPixels) {  // tiled TMA kernel when the shape allows (W % 8 == 0)
+            const int st = corr_bwd_bf16_tiled(x1, x2, gout, gx1, gx2, B, C, H, W, (cudaStream_t)stream);
+            if (st != USF_ERR_UNSUPPORTED) return st;
+        }
+        return corr_bwd_bf16(x1, x2, gout, gx1, gx2, B, C, H, W, (cudaStream_t)stream);
+    }
     return USF_ERR_BAD_ARG;
 }
 

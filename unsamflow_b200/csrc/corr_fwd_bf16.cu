@@ -39,19 +39,6 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<const uint32_t *>(&p);
 }
 
-inline bool make_bf16_map(CUtensorMap *map, const void *base, int B, int C, int H, int W, int bw, int bh, int bc) {
-    if (!tma_enabled()) return false;
-    EncodeTiledFn fn = encode_tiled_fn();
-    if (!fn || (W % 8) != 0 || ((uintptr_t)base & 15) != 0) return false;
-    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
-    const cuuint64_t strides[3] = {(cuuint64_t)W * 2, (cuuint64_t)H * W * 2, (cuuint64_t)C * H * W * 2};
-    const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bc, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 template <bool LEAKY>
 __global__ void __launch_bounds__(THREADS, 2)
 corr_fwd_tile9_tma_bf16(const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
@@ -157,7 +144,7 @@ int corr_fwd_bf16_tiled(const void *x1, const void *x2, void *out, int B, int C,
                         float slope, cudaStream_t stream) {
     if ((W % 8) != 0 || (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) & 15)) return USF_ERR_UNSUPPORTED;
     CUtensorMap m1, m2;
-    if (!make_bf16_map(&m1, x1, B, C, H, W, X1E, TH, CK) || !make_bf16_map(&m2, x2, B, C, H, W, X2E, X2R, CK))
+    if (!make_nchw_map_bf16(&m1, x1, B, C, H, W, X1E, TH, CK) || !make_nchw_map_bf16(&m2, x2, B, C, H, W, X2E, X2R, CK))
         return USF_ERR_UNSUPPORTED;
     const int tx = (W + TW - 1) / TW, ty = (H + TH - 1) / TH, ntiles = tx * ty * B;
     const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;

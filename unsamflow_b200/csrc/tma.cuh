@@ -57,6 +57,21 @@ inline bool make_nchw_map(CUtensorMap *map, const float *base, int B, int C, int
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// bf16 NCHW tensor, box [bc][bh][bw]: global strides must be multiples of 16 bytes -> W % 8 == 0
+inline bool make_nchw_map_bf16(CUtensorMap *map, const void *base, int B, int C, int H, int W, int bw, int bh,
+                               int bc) {
+    if (!tma_enabled()) return false;
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || (W % 8) != 0 || ((uintptr_t)base & 15) != 0) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)W * 2, (cuuint64_t)H * W * 2, (cuuint64_t)C * H * W * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bc, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // ---- device ----------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -85,7 +85,8 @@ def corr_bwd(x1, x2, gout, need_gx1=True, need_gx2=True, gx1=None, gx2=None):
         raise ValueError(f"dtype mismatch: {x1.dtype}, {x2.dtype}, {gout.dtype}")
     if x1.numel() == 0:
         return (torch.empty_like(x1) if need_gx1 else None, torch.empty_like(x2) if need_gx2 else None)
-    if x1.dtype == torch.bfloat16 and B * H * W > BF16_NATIVE_MAX_PIXELS:
+    if x1.dtype == torch.bfloat16 and B * H * W > BF16_NATIVE_MAX_PIXELS and W % 8 != 0:
+        # (W % 8 == 0 takes the native bf16 tiled TMA kernel, csrc/corr_bwd_bf16.cu)
         w1, w2 = corr_bwd(x1.float(), x2.float(), gout.float(), need_gx1, need_gx2)
         res = []
         for wide, dst, need in ((w1, gx1, need_gx1), (w2, gx2, need_gx2)):
