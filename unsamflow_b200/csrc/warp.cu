@@ -315,7 +315,8 @@ __device__ __forceinline__ void cswap(int &ka, float &wa, int &kb, float &wb) {
 }
 
 template <int NS, typename T>
-__global__ void __launch_bounds__(kBlock)
+// register cap: left alone, the NS = 1 form takes 128 registers and runs at a quarter of the occupancy
+__global__ void __launch_bounds__(kBlock, NS == 1 ? 3 : 4)
 warp_gx_gather(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, int N, int C, int HW, FastDiv dHW) {
     constexpr int PPB = kBlock / NS;
     // slice 0 of every pixel loads and sorts the tap list once; the other slices read it from here
@@ -593,7 +594,9 @@ const int kWarpSmallMaxHW = [] {
 }();
 
 int pick_ns(int C, int N) {
-    int ns = 1;
+    // at least two slices once there are 16 channels: one thread walking 32 channels of a level that does not
+    // fit in L2 (64x32x64x208) ran the gather at 10 % of DRAM bandwidth (ncu), two slices at twice that
+    int ns = C >= 16 ? 2 : 1;
     const long wave = 148L * 2048;
     while (ns < 32 && C >= 8 * ns && (ns < 8 ? (long)N * ns < wave : (long)N * ns * 2 <= wave)) ns *= 2;
     return ns;
