@@ -114,7 +114,7 @@ __device__ __forceinline__ float ldp(const float *__restrict__ base, int off, bo
 // case inside a training step, whose working set is far larger than L2 -- that serialised pair was the
 // limiter (1.5 TB/s on the 256x832 loss-side warp).
 template <int NS, typename T>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 5)
 warp_fwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, T *__restrict__ out, int N,
                 int C, int H, int W, int border, int rcp, FastDiv dHW, FastDiv dW) {
     constexpr int PPB = kBlock / NS;
@@ -208,7 +208,7 @@ __device__ __forceinline__ void emit_tap(const Workspace &ws, int plane0, int of
 
 // MODE 0: g_flow only.  MODE 1: (g_flow) + emit tap lists.  MODE 2: (g_flow) + atomic g_x scatter.
 template <int NS, int MODE, typename T>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, NS == 1 ? 4 : 5)  // (5 would spill the single-slice form)
 warp_bwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, const T *__restrict__ gout,
                 T *__restrict__ gx, float *__restrict__ gflow, Workspace ws, int N, int C, int H, int W,
                 int border, int rcp, FastDiv dHW, FastDiv dW) {
@@ -316,7 +316,7 @@ __device__ __forceinline__ void cswap(int &ka, float &wa, int &kb, float &wb) {
 
 template <int NS, typename T>
 // register cap: left alone, the NS = 1 form takes 128 registers and runs at a quarter of the occupancy
-__global__ void __launch_bounds__(kBlock, NS == 1 ? 3 : 4)
+__global__ void __launch_bounds__(kBlock, NS == 1 ? 3 : 5)
 warp_gx_gather(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, int N, int C, int HW, FastDiv dHW) {
     constexpr int PPB = kBlock / NS;
     // slice 0 of every pixel loads and sorts the tap list once; the other slices read it from here
