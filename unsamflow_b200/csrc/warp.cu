@@ -113,10 +113,14 @@ __device__ __forceinline__ float ldp(const float *__restrict__ base, int off, bo
 // memory round trip per pixel instead of two back-to-back (flow, then taps).  With cold inputs -- the normal
 // case inside a training step, whose working set is far larger than L2 -- that serialised pair was the
 // limiter (1.5 TB/s on the 256x832 loss-side warp).
-template <int NS, typename T>
+// CC > 0: channel count known at compile time (the 3-channel loss-side warp): the channel loop unrolls
+// completely and all 12 taps are in flight at once; with a run-time C = 3 the unroll-by-4 loop degenerates to
+// its one-channel-at-a-time remainder, i.e. three dependent round trips.
+template <int NS, typename T, int CC = 0>
 __global__ void __launch_bounds__(kBlock, 5)
 warp_fwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, T *__restrict__ out, int N,
-                int C, int H, int W, int border, int rcp, FastDiv dHW, FastDiv dW) {
+                int Crt, int H, int W, int border, int rcp, FastDiv dHW, FastDiv dW) {
+    const int C = CC ? CC : Crt;
     constexpr int PPB = kBlock / NS;
     constexpr int UN = NS >= 4 ? 8 : 4;  // channels in flight per thread
     const int pl = threadIdx.x % PPB, cs = threadIdx.x / PPB;
@@ -146,7 +150,7 @@ warp_fwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, T *__re
         const T *p0 = x + ((size_t)b * C + cs) * HW + t.o_nw;
         const T *p1 = p0 + W;
         T *o = out + ((size_t)b * C + cs) * HW + rem;
-#pragma unroll UN
+#pragma unroll(CC ? CC : UN)
         for (int c = cs; c < C; c += NS, p0 += step, p1 += step, o += step) {
             float acc = (t.k_nw ? ldf(p0) : 0.f) * nw;
             acc = fmaf(t.k_ne ? ldf(p0 + 1) : 0.f, ne, acc);
@@ -207,11 +211,12 @@ __device__ __forceinline__ void emit_tap(const Workspace &ws, int plane0, int of
 }
 
 // MODE 0: g_flow only.  MODE 1: (g_flow) + emit tap lists.  MODE 2: (g_flow) + atomic g_x scatter.
-template <int NS, int MODE, typename T>
+template <int NS, int MODE, typename T, int CC = 0>
 __global__ void __launch_bounds__(kBlock, NS == 1 ? 4 : 5)  // (5 would spill the single-slice form)
 warp_bwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, const T *__restrict__ gout,
-                T *__restrict__ gx, float *__restrict__ gflow, Workspace ws, int N, int C, int H, int W,
+                T *__restrict__ gx, float *__restrict__ gflow, Workspace ws, int N, int Crt, int H, int W,
                 int border, int rcp, FastDiv dHW, FastDiv dW) {
+    const int C = CC ? CC : Crt;  // see warp_fwd_kernel
     constexpr int PPB = kBlock / NS;
     constexpr int UN = NS >= 4 ? 8 : 4;  // channels in flight per thread
     __shared__ float red[2][NS][PPB];
@@ -256,7 +261,7 @@ warp_bwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, const T
             const T *p1 = p0 + W;
             T *q0 = (MODE == 2) ? gx + ((size_t)b * C + cs) * HW + t.o_nw : nullptr;
             if (gflow != nullptr || MODE == 2) {
-#pragma unroll UN
+#pragma unroll(CC ? CC : UN)
                 for (int c = cs; c < C; c += NS, gb += step, p0 += step, p1 += step) {
                     const float go = ldf(gb);
                     if (gflow != nullptr) {
@@ -637,6 +642,12 @@ static int warp_fwd_t(const T *x, const float *flow, T *out, int B, int C, int H
         const int res = resident_ctas((const void *)warp_fwd_kernel<NS, T>);                \
         warp_fwd_kernel<NS, T><<<blocks < res ? blocks : res, kBlock, 0, stream>>>(x, flow, out, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W)); \
     }
+    if (ns == 1 && C == 3) {  // loss-side warp of an RGB image
+        const int res = resident_ctas((const void *)warp_fwd_kernel<1, T, 3>);
+        warp_fwd_kernel<1, T, 3><<<blocks < res ? blocks : res, kBlock, 0, stream>>>(
+            x, flow, out, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W));
+        return note_launch(cudaGetLastError());
+    }
     switch (ns) {
         case 32: USF_LAUNCH(32); break;
         case 16: USF_LAUNCH(16); break;
@@ -679,6 +690,12 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
     const int blocks = (N + kBlock / ns - 1) / (kBlock / ns);
     Workspace ws = {};
     if (gx == nullptr) {
+        if (ns == 1 && C == 3) {  // loss-side warp of an RGB image: gradient wrt the flow only
+            const int res = resident_ctas((const void *)warp_bwd_kernel<1, 0, T, 3>);
+            warp_bwd_kernel<1, 0, T, 3><<<blocks < res ? blocks : res, kBlock, 0, stream>>>(
+                x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W));
+            return note_launch(cudaGetLastError());
+        }
         return note_launch(launch_bwd<0, T>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
     }
     if (flags & USF_FLAG_WARP_BWD_ATOMIC) {
