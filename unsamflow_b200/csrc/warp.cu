@@ -122,7 +122,7 @@ warp_fwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, T *__re
                 int Crt, int H, int W, int border, int rcp, FastDiv dHW, FastDiv dW) {
     const int C = CC ? CC : Crt;
     constexpr int PPB = kBlock / NS;
-    constexpr int UN = NS >= 4 ? 8 : 4;  // channels in flight per thread
+    constexpr int UN = (NS >= 4 && NS <= 8) ? 8 : 4;  // channels in flight per thread (16+ slices: 4-6 channels each)
     const int pl = threadIdx.x % PPB, cs = threadIdx.x / PPB;
     const int HW = H * W, stride = gridDim.x * PPB;
     int p = blockIdx.x * PPB + pl;
@@ -218,7 +218,7 @@ warp_bwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, const T
                 int border, int rcp, FastDiv dHW, FastDiv dW) {
     const int C = CC ? CC : Crt;  // see warp_fwd_kernel
     constexpr int PPB = kBlock / NS;
-    constexpr int UN = NS >= 4 ? 8 : 4;  // channels in flight per thread
+    constexpr int UN = (NS >= 4 && NS <= 8) ? 8 : 4;  // channels in flight per thread (16+ slices: 4-6 channels each)
     __shared__ float red[2][NS][PPB];
     const int pl = threadIdx.x % PPB, cs = threadIdx.x / PPB;
     const int HW = H * W, stride = gridDim.x * PPB;
