@@ -432,9 +432,20 @@ warp_bwd_small(const T *__restrict__ x, const float *__restrict__ flow, const T 
 
     for (int i = tid; i <= PPB; i += kBlock) s_cnt[i] = 0;
     __syncthreads();
-    for (int src = tid; src < HW; src += kBlock) {
+    // the image's flow first (<= 4 pixels per thread, all requests in flight together), then the taps
+    float fu[4], fv[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int src = tid + k * kBlock;
+        fu[k] = src < HW ? __ldg(fl + src) : 0.f;
+        fv[k] = src < HW ? __ldg(fl + HW + src) : 0.f;
+    }
+    #pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+        const int src = tid + k4 * kBlock;
+        if (src >= HW) break;
         const int y = dW.div(src), xo = src - y * W;
-        const Taps t = make_taps(y, xo, __ldg(fl + src), __ldg(fl + HW + src), H, W, border, rcp);
+        const Taps t = make_taps(y, xo, fu[k4], fv[k4], H, W, border, rcp);
         const int off[4] = {t.o_nw, t.o_ne, t.o_sw, t.o_se};
         const bool ok[4] = {t.k_nw, t.k_ne, t.k_sw, t.k_se};
         const float wt[4] = {t.ex * t.ey, t.wx * t.ey, t.ex * t.wy, t.wx * t.wy};
@@ -741,10 +752,10 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
 #undef USF_LAUNCH
     st = note_launch(cudaGetLastError());
     if (st != USF_OK) return st;
-    // fixed grid (the entry count lives on the device), sized for the worst case of this shape: up to 8 CTAs
-    // per SM, grid-stride over entries x channels
+    // fixed grid (the entry count lives on the device), sized for the worst case of this shape: up to 2 CTAs
+    // per SM (the list is normally empty or short), grid-stride over entries x channels
     long ovf_blocks = ((long)4 * N * C + 16L * kBlock - 1) / (16L * kBlock);
-    ovf_blocks = ovf_blocks < 16 ? 16 : (ovf_blocks > 148 * 8 ? 148 * 8 : ovf_blocks);
+    ovf_blocks = ovf_blocks < 16 ? 16 : (ovf_blocks > 148 * 2 ? 148 * 2 : ovf_blocks);
     warp_gx_overflow<T><<<(int)ovf_blocks, kBlock, 0, stream>>>(gout, gx, ws, 4 * N, C, HW);
     return note_launch(cudaGetLastError());
 }
