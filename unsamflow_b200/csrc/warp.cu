@@ -117,7 +117,7 @@ __device__ __forceinline__ float ldp(const float *__restrict__ base, int off, bo
 // completely and all 12 taps are in flight at once; with a run-time C = 3 the unroll-by-4 loop degenerates to
 // its one-channel-at-a-time remainder, i.e. three dependent round trips.
 template <int NS, typename T, int CC = 0>
-__global__ void __launch_bounds__(kBlock, 5)
+__global__ void __launch_bounds__(kBlock, CC ? 6 : 5)
 warp_fwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, T *__restrict__ out, int N,
                 int Crt, int H, int W, int border, int rcp, FastDiv dHW, FastDiv dW) {
     const int C = CC ? CC : Crt;
@@ -212,7 +212,7 @@ __device__ __forceinline__ void emit_tap(const Workspace &ws, int plane0, int of
 
 // MODE 0: g_flow only.  MODE 1: (g_flow) + emit tap lists.  MODE 2: (g_flow) + atomic g_x scatter.
 template <int NS, int MODE, typename T, int CC = 0>
-__global__ void __launch_bounds__(kBlock, NS == 1 ? 4 : 5)  // (5 would spill the single-slice form)
+__global__ void __launch_bounds__(kBlock, (NS == 1 && !CC) ? 4 : 5)  // (5 would spill the generic single-slice form)
 warp_bwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, const T *__restrict__ gout,
                 T *__restrict__ gx, float *__restrict__ gflow, Workspace ws, int N, int Crt, int H, int W,
                 int border, int rcp, FastDiv dHW, FastDiv dW) {
