@@ -535,6 +535,8 @@ inline bool mixed_enabled() {
 
 // CTAs of the 8-channel-per-thread configuration; below ~3/4 of a wave (2 CTAs/SM) the 4-channel one is used
 inline bool thin_grid(int B, int C, int H, int W, int ngrad) {
+    static const int force = [] { const char *e = getenv("USF_BWD_THIN"); return e ? atoi(e) : -1; }();
+    if (force >= 0) return force != 0;
     const long ctas = (long)((W + TW - 1) / TW) * ((H + TH - 1) / TH) * B * ((C + CG - 1) / CG) * ngrad;
     return ctas * 4 < 148L * 2 * 3;
 }
