@@ -449,15 +449,19 @@ def test_corr_kernels_are_bit_deterministic_under_load(usf):
     a stage released before its loads had landed once showed up as rare, large errors in gx2)."""
     ops = usf.ops_mod
     g = torch.Generator().manual_seed(7)
-    shape = (8, 32, 64, 208)
-    x1, x2 = torch.randn(shape, generator=g).cuda(), torch.randn(shape, generator=g).cuda()
-    go = torch.randn(8, 81, 64, 208, generator=g).cuda()
-    o0 = ops.corr_fwd(x1, x2).clone()
-    a0, b0 = (t.clone() for t in ops.corr_bwd(x1, x2, go))
-    for _ in range(50):
-        a, b = ops.corr_bwd(x1, x2, go)
-        assert torch.equal(a, a0) and torch.equal(b, b0)
-        assert torch.equal(ops.corr_fwd(x1, x2), o0)
+    # mixed-tile TMA backward, 8x32 tiles, the 4-channel thin-grid form at 3 CTAs/SM (where the stage-release
+    # race resurfaced before release_stage_reads() got its fence: 5 of 300 runs differed), whole-image kernels
+    for shape, runs in [((8, 32, 64, 208), 50), ((8, 64, 32, 104), 50), ((8, 96, 16, 52), 150),
+                        ((1, 64, 32, 104), 150), ((8, 128, 8, 26), 50)]:
+        B, C, H, W = shape
+        x1, x2 = torch.randn(shape, generator=g).cuda(), torch.randn(shape, generator=g).cuda()
+        go = torch.randn(B, 81, H, W, generator=g).cuda()
+        o0 = ops.corr_fwd(x1, x2).clone()
+        a0, b0 = (t.clone() for t in ops.corr_bwd(x1, x2, go))
+        for _ in range(runs):
+            a, b = ops.corr_bwd(x1, x2, go)
+            assert torch.equal(a, a0) and torch.equal(b, b0), shape
+            assert torch.equal(ops.corr_fwd(x1, x2), o0), shape
 
 
 # --------------------------------------------------------------------------------------------

@@ -55,6 +55,16 @@ __device__ __forceinline__ void atomic_addf(bf16 *p, float v) { atomicAdd(p, __f
 
 __device__ __forceinline__ float4 lds128(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 
+// Release of a shared-memory stage back to the TMA producer.  The fence makes every lane's outstanding
+// shared-memory reads of the stage COMPLETE before lane 0 arrives on the "empty" barrier: an arrive that merely
+// follows the LDS instructions in program order does not wait for their data, and ptxas is free to sink the
+// FFMAs that consume them below the arrive (it does, in the 3-CTA/SM backward) -- the producer's next TMA
+// write then races with loads still in flight (seen as a few non-reproducible runs out of hundreds).
+__device__ __forceinline__ void release_stage_reads() {
+    __threadfence_block();  // MEMBAR.CTA: waits for the outstanding loads
+    __syncwarp();
+}
+
 __device__ __forceinline__ void st_global_cs(float *p, float v) {
     asm volatile("st.global.cs.f32 [%0], %1;\n" ::"l"(p), "f"(v) : "memory");
 }

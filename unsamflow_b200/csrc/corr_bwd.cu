@@ -328,11 +328,11 @@ __device__ __forceinline__ void bwd_tile(unsigned char *smem_raw, const CUtensor
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(g[dx][i], w[dx + i], acc[c][i]);
             if (c == 0) {
-                // Release the G stage only after the first channel's FFMAs have CONSUMED every g value:
-                // an arrive issued right after the LDS instructions does not wait for their data, and the
-                // producer's next TMA write then races with loads still in flight (seen as rare, large
-                // errors in gx2 at 8x32x64x208).
-                __syncwarp();
+                // Release the G stage after the first channel's FFMAs (which use every g value) and behind a
+                // fence: an arrive that merely follows the LDS instructions does not wait for their data, and
+                // the producer's next TMA write then races with loads still in flight (seen as rare, large
+                // errors in gx2 at 8x32x64x208; see release_stage_reads in common.cuh).
+                release_stage_reads();
                 if (lane == 0) mbar_arrive(&gempty[s]);
             }
         }
@@ -468,7 +468,7 @@ __device__ __forceinline__ void bwd_tile_sq(unsigned char *smem_raw, const CUten
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(g[dx][i], w[dx + i], acc[c][i]);
             if (c == 0) {  // release the G stage only after its values have been consumed (see bwd_tile)
-                __syncwarp();
+                release_stage_reads();
                 if (lane == 0) mbar_arrive(&gempty[s]);
             }
         }

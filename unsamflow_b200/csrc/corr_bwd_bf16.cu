@@ -152,7 +152,7 @@ __device__ __forceinline__ void bwd_tile(unsigned char *smem_raw, const CUtensor
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(g[dx][i], v[4 + dx + i], acc[c][i]);
             if (c == 0) {  // release the G stage only after its values have been consumed (see corr_bwd.cu)
-                __syncwarp();
+                release_stage_reads();
                 if (lane == 0) mbar_arrive(&gempty[s]);
             }
         }

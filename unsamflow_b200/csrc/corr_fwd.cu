@@ -394,7 +394,7 @@ corr_fwd_tile9_tma(const __grid_constant__ CUtensorMap m1, const __grid_constant
 #pragma unroll 2
                 for (int c = 0; c < CK; ++c) fma_channel(acc, p1 + c * TH * X1S, p2 + c * A_ROWS2 * X2S);
             }
-            __syncwarp();
+            release_stage_reads();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }
         store_tile<LEAKY>(acc, out, b, warp, ty * TH, tx * TW, r, q, H, W, rc, slope);
@@ -456,7 +456,7 @@ corr_fwd_splitc_tma(const __grid_constant__ CUtensorMap m1, const __grid_constan
         mbar_wait(&full_bar[s], (k / TB_NST) & 1);
         const float *st = reinterpret_cast<const float *>(smem_raw + s * TB_STAGE_BYTES);
         fma_channel(acc, st + (warp * TH + r) * X1S + 8 * q, st + CK * TH * X1S + (warp * TH + r) * X2S + 8 * q);
-        __syncwarp();
+        release_stage_reads();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
     // all 8 consumer warps are past their last stage read -> reuse the ring for the reduction

@@ -114,7 +114,7 @@ corr_fwd_tile9_tma_bf16(const __grid_constant__ CUtensorMap m1, const __grid_con
 #pragma unroll
                     for (int i = 0; i < 8; ++i) acc[dx][i] = fmaf(a[i], e[dx + i], acc[dx][i]);
             }
-            __syncwarp();
+            release_stage_reads();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }
 

@@ -177,7 +177,10 @@ corr_fwd_small(const __grid_constant__ CUtensorMap m1, const __grid_constant__ C
     uint32_t phase = 0;
     for (int c0 = 0; c0 < C; c0 += CK) {
         const int ck = min(CK, C - c0);
-        if (c0) __syncthreads();
+        if (c0) {  // the slabs are about to be overwritten (by TMA on the fast path): reads must have completed
+            __threadfence_block();
+            __syncthreads();
+        }
         if (tma) {
             if (tid == 0) {
                 mbar_expect_tx(&fill_bar, 2u * CK * S * 4u);
