@@ -1,9 +1,11 @@
-// corr_direct.cu -- cost volume fwd/bwd for TINY pyramid levels (a few thousand pixels or less).
+// corr_direct.cu -- cost volume fwd/bwd straight from global memory, for what no other kernel takes.
 //
-// The coarsest PWC-Lite levels (KITTI 4x13 and 8x26, models/pwclite.py:295 levels 0-1) hold
-// 52..208 pixels per image: the whole problem fits in L1/L2, has odd widths (no TMA, no 16-byte
-// vectors) and is pure launch/latency.  Tiling through shared memory only adds barriers there,
-// so these kernels read global memory directly (coalesced along x, everything L1/L2 resident):
+// Dispatch order of the correlation (api.cu, corr_fwd.cu, corr_bwd.cu): whole images of <= 256 pixels go
+// to corr_small.cu (KITTI 4x13 / 8x26), widths that TMA can address to the tiled kernels, large odd widths
+// to the cp.async tiled kernels.  What is left comes here: SMALL shapes (B*H*W <= 4096) above 256 pixels per
+// image whose width is not a multiple of 4 (fp32) -- e.g. crops like 9x33 -- and bf16 shapes whose width is
+// not a multiple of 8.  Everything is L1/L2 resident at these sizes and tiling through shared memory only
+// adds barriers, so these kernels read global memory directly (coalesced along x):
 //   fwd:  32 outputs x 8 channel slices per CTA (one warp per slice), partial sums reduced in a fixed
 //         order through shared memory: short dependent-load chains, plenty of threads.
 //   bwd:  one thread = 4 channels of one pixel x 3 displacement rows, BOTH gradients as gathers.
@@ -161,8 +163,8 @@ int corr_bwd_direct_f32(const float *x1, const float *x2, const float *gout, flo
                         int H, int W, cudaStream_t stream) {
     return bwd_direct<float>(x1, x2, gout, gx1, gx2, B, C, H, W, stream);
 }
-// bf16 storage, fp32 accumulate: every shape is handled by the direct kernels (correct everywhere; the
-// tiled / tensor-core bf16 kernels for the large levels are round-2 work)
+// bf16 storage, fp32 accumulate: the fallback behind corr_small.cu and the tiled bf16 TMA kernels
+// (corr_fwd_bf16.cu / corr_bwd_bf16.cu, W % 8 == 0); correct for every shape, slow for large ones
 int corr_fwd_bf16(const void *x1, const void *x2, void *out, int B, int C, int H, int W, unsigned flags, float slope,
                   cudaStream_t stream) {
     return fwd_direct<bf16>((const bf16 *)x1, (const bf16 *)x2, (bf16 *)out, B, C, H, W, flags, slope, stream);

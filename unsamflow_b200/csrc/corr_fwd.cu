@@ -517,8 +517,9 @@ int corr_fwd_direct_f32(const float *, const float *, float *, int, int, int, in
 
 int corr_fwd_f32(const float *x1, const float *x2, float *out, int B, int C, int H, int W, unsigned flags,
                  float slope, cudaStream_t stream) {
-    // tiny levels (KITTI 4x13, 8x26): latency-bound, L1/L2 resident -> direct kernel (corr_direct.cu)
-    // (widths TMA can address go to the tiled kernels even when small)
+    // small odd-width shapes above 256 pixels per image (whole images <= 256 pixels never get here, api.cu sends
+    // them to corr_small.cu): L1/L2 resident -> direct kernel (corr_direct.cu); widths TMA can address go to the
+    // tiled kernels even when small
     if ((long)B * H * W <= kDirectMaxPixels && (W % 4) != 0) return corr_fwd_direct_f32(x1, x2, out, B, C, H, W, flags, slope, stream);
     const bool vec = (W % 4 == 0) && (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) % 16 == 0);
     const int tx = (W + TW - 1) / TW, ty = (H + TH - 1) / TH;
