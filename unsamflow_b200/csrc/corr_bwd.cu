@@ -198,6 +198,10 @@ corr_bwd_gather(const float *__restrict__ xin, const float *__restrict__ gout, f
 // compile-time constant in the unrolled consumer loop, so the unaligned window is read as 2-3
 // aligned LDS.128 and selected with static register indices.
 // ===========================================================================================
+// channel after which a consumer warp releases the G stage (fence + arrive): early enough for the producer to
+// refill ahead, late enough that the fence finds the stage's loads already complete (measured: after channel
+// 0 -> 47.6 us, 1 -> 46.0, 3 -> 46.1 at 8x32x64x208; 15.0 / 14.7 / 14.2 us in the 4-channel form at 8x96x16x52)
+constexpr int kRelAt = 3;
 constexpr int NCW = CG / CT;                                 // 4 consumer warps
 constexpr int T_THREADS = 32 * (NCW + 1);                    // + 1 producer warp
 constexpr int NBAR = NCW + 4;                                // xfull[4], gfull[2], gempty[2]
@@ -327,9 +331,9 @@ __device__ __forceinline__ void bwd_tile(unsigned char *smem_raw, const CUtensor
             for (int dx = 0; dx < kD; ++dx)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(g[dx][i], w[dx + i], acc[c][i]);
-            if (c == 0) {
-                // Release the G stage after the first channel's FFMAs (which use every g value) and behind a
-                // fence: an arrive that merely follows the LDS instructions does not wait for their data, and
+            if (c == kRelAt) {
+                // Release the G stage after a few channels' FFMAs (every channel uses every g value) and behind
+                // a fence: an arrive that merely follows the LDS instructions does not wait for their data, and
                 // the producer's next TMA write then races with loads still in flight (seen as rare, large
                 // errors in gx2 at 8x32x64x208; see release_stage_reads in common.cuh).
                 release_stage_reads();
@@ -467,7 +471,7 @@ __device__ __forceinline__ void bwd_tile_sq(unsigned char *smem_raw, const CUten
             for (int dx = 0; dx < kD; ++dx)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(g[dx][i], w[dx + i], acc[c][i]);
-            if (c == 0) {  // release the G stage only after its values have been consumed (see bwd_tile)
+            if (c == kRelAt) {  // release the G stage only after its values have been consumed (see bwd_tile)
                 release_stage_reads();
                 if (lane == 0) mbar_arrive(&gempty[s]);
             }
