@@ -151,7 +151,7 @@ __device__ __forceinline__ void bwd_tile(unsigned char *smem_raw, const CUtensor
             for (int dx = 0; dx < kD; ++dx)
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(g[dx][i], v[4 + dx + i], acc[c][i]);
-            if (c == 0) {  // release the G stage only after its values have been consumed (see corr_bwd.cu)
+            if (c == 3) {  // release the G stage: fence + arrive, placed as in corr_bwd.cu (kRelAt)
                 release_stage_reads();
                 if (lane == 0) mbar_arrive(&gempty[s]);
             }
