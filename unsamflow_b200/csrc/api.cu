@@ -37,6 +37,14 @@ long kDirectMaxPixels = [] {
     return e ? atol(e) : 4096L;
 }();
 
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("USF_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 static thread_local int tl_cuda_error = 0;
 static thread_local unsigned long long tl_launches = 0;
 

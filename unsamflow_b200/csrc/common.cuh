@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "../../include/unsamflow_b200.h"
 
 namespace usf {
@@ -21,6 +23,30 @@ void note_cuda_error(cudaError_t e);
 // Opt a kernel into `smem_bytes` of dynamic shared memory (+ max shared carve-out) once per (kernel, device).
 // cudaFuncSetAttribute is per device, so a process that drives several GPUs is handled too.
 cudaError_t ensure_smem(const void *kernel, int smem_bytes);
+
+// ---- launches ---------------------------------------------------------------
+// Every hot-path kernel is launched with programmatic stream serialization and starts with griddepcontrol.wait:
+// the semantics are those of plain stream order (the wait returns when the preceding kernel of the stream has
+// completed and flushed), but the launch itself -- grid setup, parameter and tensor-map upload, CTA dispatch -- no
+// longer waits for the predecessor to drain, which is a microsecond or two per dependent kernel in a chain of
+// ~30.  USF_PDL=0 launches without the attribute (the wait is then a no-op).
+bool pdl_enabled();  // api.cu
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t usf_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---- cp.async (LDGSTS) ------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

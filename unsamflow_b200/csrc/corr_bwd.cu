@@ -368,6 +368,7 @@ corr_bwd_gather_tma(const __grid_constant__ CUtensorMap mx1, const __grid_consta
                     const __grid_constant__ CUtensorMap mx2, const __grid_constant__ CUtensorMap mg2,
                     float *__restrict__ gx1, float *__restrict__ gx2, int C, int H, int W, int ngroups, int nz,
                     float rc) {
+    pdl_wait();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     int z = blockIdx.z;
     const bool second = (gx1 == nullptr) || z >= nz;
@@ -500,6 +501,7 @@ corr_bwd_gather_tma_mixed(const __grid_constant__ CUtensorMap mx1, const __grid_
                           const __grid_constant__ CUtensorMap mx2, const __grid_constant__ CUtensorMap mg2,
                           float *__restrict__ gx1, float *__restrict__ gx2, int C, int H, int W, int ngroups, int nz,
                           int t32x, int t32y, int t16x, int t16y, float rc) {
+    pdl_wait();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     int id = blockIdx.x;
     const int n2 = t32x * t32y * nz;
@@ -523,7 +525,7 @@ cudaError_t launch_tma(const CUtensorMap &mx1, const CUtensorMap &mg1, const CUt
     const int ngroups = (C + NCW * CTT - 1) / (NCW * CTT);
     const int nz = B * ngroups;
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, nz * ((gx1 && gx2) ? 2 : 1));
-    corr_bwd_gather_tma<CTT><<<grid, T_THREADS, SM, stream>>>(mx1, mg1, mx2, mg2, gx1, gx2, C, H, W, ngroups, nz,
+    usf_launch(corr_bwd_gather_tma<CTT>, dim3(grid), dim3(T_THREADS), SM, stream, mx1, mg1, mx2, mg2, gx1, gx2, C, H, W, ngroups, nz,
                                                               1.0f / (float)C);
     return cudaGetLastError();
 }
@@ -584,7 +586,7 @@ int corr_bwd_f32(const float *x1, const float *x2, const float *gout, float *gx1
                 make_nchw_map(&mx2, x1, B, C, H, W, XS, XR, CT) && make_nchw_map(&mg2, gout, B, kK, H, W, XS, TH, kD)) {
                 constexpr int SM = GTile<true, CT>::kSmem > SQ_SMEM ? GTile<true, CT>::kSmem : SQ_SMEM;
                 if (cudaError_t once = ensure_smem((const void *)corr_bwd_gather_tma_mixed, SM)) return note_launch(once);
-                corr_bwd_gather_tma_mixed<<<(unsigned)mix, T_THREADS, SM, stream>>>(
+                usf_launch(corr_bwd_gather_tma_mixed, dim3((unsigned)mix), dim3(T_THREADS), SM, stream, 
                     mx1, mg1, mx2, mg2, gx1, gx2, C, H, W, ngroups, nz, t32x, t32y, t16x, t16y, 1.0f / (float)C);
                 return note_launch(cudaGetLastError());
             }

@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(TA_THREADS, T9Cfg<PIPE>::kMinBlocks)
 corr_fwd_tile9_tma(const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
                    float *__restrict__ out, int C, int H, int W, int tiles_x, int tiles_y, int ntiles, float rc,
                    float slope) {
+    pdl_wait();
     constexpr int NS = T9Cfg<PIPE>::kStages;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + NS * TA_STAGE_BYTES);
@@ -412,6 +413,7 @@ template <bool LEAKY>
 __global__ void __launch_bounds__(TB_THREADS, 2)
 corr_fwd_splitc_tma(const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
                     float *__restrict__ out, int C, int H, int W, float rc, float slope) {
+    pdl_wait();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[TB_NST], empty_bar[TB_NST];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -491,20 +493,20 @@ cudaError_t launch_tma(bool splitc, const CUtensorMap &m1, const CUtensorMap &m2
     if (splitc) {
         cudaError_t once = ensure_smem((const void *)corr_fwd_splitc_tma<LEAKY>, TB_SMEM);
         if (once != cudaSuccess) return once;
-        corr_fwd_splitc_tma<LEAKY><<<dim3(tx, ty, B * kD), TB_THREADS, TB_SMEM, stream>>>(m1, m2b, out, C, H, W, rc, slope);
+        usf_launch(corr_fwd_splitc_tma<LEAKY>, dim3(dim3(tx, ty, B * kD)), dim3(TB_THREADS), TB_SMEM, stream, m1, m2b, out, C, H, W, rc, slope);
     } else {
         const int ntiles = tx * ty * B;
         if (ntiles * 2 <= 3 * 148) {  // at most 1.5 tiles per SM: one pipelined CTA per SM
             cudaError_t once = ensure_smem((const void *)corr_fwd_tile9_tma<LEAKY, true>, T9Cfg<true>::kSmem);
             if (once != cudaSuccess) return once;
             const int grid = ntiles < 148 ? ntiles : 148;
-            corr_fwd_tile9_tma<LEAKY, true><<<grid, TA_THREADS, T9Cfg<true>::kSmem, stream>>>(
+            usf_launch((corr_fwd_tile9_tma<LEAKY, true>), dim3(grid), dim3(TA_THREADS), T9Cfg<true>::kSmem, stream, 
                 m1, m2a, out, C, H, W, tx, ty, ntiles, rc, slope);
         } else {
             cudaError_t once = ensure_smem((const void *)corr_fwd_tile9_tma<LEAKY, false>, T9Cfg<false>::kSmem);
             if (once != cudaSuccess) return once;
             const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;
-            corr_fwd_tile9_tma<LEAKY, false><<<grid, TA_THREADS, T9Cfg<false>::kSmem, stream>>>(
+            usf_launch((corr_fwd_tile9_tma<LEAKY, false>), dim3(grid), dim3(TA_THREADS), T9Cfg<false>::kSmem, stream, 
                 m1, m2a, out, C, H, W, tx, ty, ntiles, rc, slope);
         }
     }

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(kMaxThreads)
 corr_fwd_small(const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
                const T *__restrict__ x1, const T *__restrict__ x2, T *__restrict__ out, int C, int H, int W, int RB,
                int lgP, int NG, int CK, int S, int tma, float rc, float slope) {
+    pdl_wait();
     extern __shared__ __align__(1024) float sm[];
     __shared__ uint64_t fill_bar;
     const int tid = threadIdx.x, nthr = blockDim.x, P = 1 << lgP;
@@ -317,6 +318,7 @@ template <int PX, typename T>
 __global__ void __launch_bounds__(kMaxThreads)
 corr_bwd_small(const T *__restrict__ x1, const T *__restrict__ x2, const T *__restrict__ gout, T *__restrict__ gx1,
                T *__restrict__ gx2, int C, int H, int W, int lgP, int NGC, int bulk, float rc) {
+    pdl_wait();
     extern __shared__ __align__(1024) float sm[];
     __shared__ uint64_t fill_bar;
     const int tid = threadIdx.x, nthr = blockDim.x, P = 1 << lgP;
@@ -432,11 +434,11 @@ cudaError_t launch_fwd(const T *x1, const T *x2, T *out, int B, int C, int H, in
     cudaError_t e;
     if (flags & USF_FLAG_LEAKY_RELU) {
         if ((e = ensure_smem((const void *)corr_fwd_small<PX, true, T>, (int)smem)) != cudaSuccess) return e;
-        corr_fwd_small<PX, true, T><<<grid, P * NG, smem, stream>>>(m1, m2, x1, x2, out, C, H, W, RB, lgP, NG, CK, S,
+        usf_launch((corr_fwd_small<PX, true, T>), dim3(grid), dim3(P * NG), smem, stream, m1, m2, x1, x2, out, C, H, W, RB, lgP, NG, CK, S,
                                                                     tma, rc, slope);
     } else {
         if ((e = ensure_smem((const void *)corr_fwd_small<PX, false, T>, (int)smem)) != cudaSuccess) return e;
-        corr_fwd_small<PX, false, T><<<grid, P * NG, smem, stream>>>(m1, m2, x1, x2, out, C, H, W, RB, lgP, NG, CK, S,
+        usf_launch((corr_fwd_small<PX, false, T>), dim3(grid), dim3(P * NG), smem, stream, m1, m2, x1, x2, out, C, H, W, RB, lgP, NG, CK, S,
                                                                      tma, rc, slope);
     }
     return cudaGetLastError();
@@ -457,7 +459,7 @@ cudaError_t launch_bwd(const T *x1, const T *x2, const T *gout, T *gx1, T *gx2, 
     cudaError_t e = ensure_smem((const void *)corr_bwd_small<PX, T>, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((C + CS - 1) / CS, B, ngrad);
-    corr_bwd_small<PX, T><<<grid, NGC * P, smem, stream>>>(x1, x2, gout, gx1, gx2, C, H, W, lgP, NGC,
+    usf_launch((corr_bwd_small<PX, T>), dim3(grid), dim3(NGC * P), smem, stream, x1, x2, gout, gx1, gx2, C, H, W, lgP, NGC,
                                                            tma_fill_ok<T>(HW, x1, x2, gout), 1.0f / (float)C);
     return cudaGetLastError();
 }

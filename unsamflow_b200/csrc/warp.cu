@@ -120,6 +120,7 @@ template <int NS, typename T, int CC = 0>
 __global__ void __launch_bounds__(kBlock, CC ? 6 : 5)
 warp_fwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, T *__restrict__ out, int N,
                 int Crt, int H, int W, int border, int rcp, FastDiv dHW, FastDiv dW) {
+    pdl_wait();
     const int C = CC ? CC : Crt;
     constexpr int PPB = kBlock / NS;
     constexpr int UN = (NS >= 4 && NS <= 8) ? 8 : 4;  // channels in flight per thread (16+ slices: 4-6 channels each)
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(kBlock, (NS == 1 && !CC) ? 4 : 5)  // (5 would
 warp_bwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, const T *__restrict__ gout,
                 T *__restrict__ gx, float *__restrict__ gflow, Workspace ws, int N, int Crt, int H, int W,
                 int border, int rcp, FastDiv dHW, FastDiv dW) {
+    pdl_wait();
     const int C = CC ? CC : Crt;  // see warp_fwd_kernel
     constexpr int PPB = kBlock / NS;
     constexpr int UN = (NS >= 4 && NS <= 8) ? 8 : 4;  // channels in flight per thread (16+ slices: 4-6 channels each)
@@ -323,6 +325,7 @@ template <int NS, typename T>
 // register cap: left alone, the NS = 1 form takes 128 registers and runs at a quarter of the occupancy
 __global__ void __launch_bounds__(kBlock, NS == 1 ? 3 : 5)
 warp_gx_gather(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, int N, int C, int HW, FastDiv dHW) {
+    pdl_wait();
     constexpr int PPB = kBlock / NS;
     // slice 0 of every pixel loads and sorts the tap list once; the other slices read it from here
     __shared__ int s_src[NS > 1 ? kSlots : 1][NS > 1 ? PPB : 1];
@@ -416,6 +419,7 @@ __global__ void __launch_bounds__(kBlock)
 warp_bwd_small(const T *__restrict__ x, const float *__restrict__ flow, const T *__restrict__ gout,
                T *__restrict__ gx, float *__restrict__ gflow, int C, int H, int W, int border, int rcp,
                FastDiv dW, FastDiv dBpi) {
+    pdl_wait();
     constexpr int PPB = kBlock / NS;
     extern __shared__ __align__(16) int sm_i[];
     const int HW = H * W, cap = 4 * HW;
@@ -588,6 +592,7 @@ warp_bwd_small(const T *__restrict__ x, const float *__restrict__ flow, const T 
 template <typename T>
 __global__ void __launch_bounds__(kBlock)
 warp_gx_overflow(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, int cap, int C, int HW) {
+    pdl_wait();
     const int n = min(ws.ovf_n[0], cap);
     const long total = (long)n * C;
     for (long it = (long)blockIdx.x * kBlock + threadIdx.x; it < total; it += (long)gridDim.x * kBlock) {
@@ -651,11 +656,11 @@ static int warp_fwd_t(const T *x, const float *flow, T *out, int B, int C, int H
 #define USF_LAUNCH(NS)                                                                      \
     {                                                                                       \
         const int res = resident_ctas((const void *)warp_fwd_kernel<NS, T>);                \
-        warp_fwd_kernel<NS, T><<<blocks < res ? blocks : res, kBlock, 0, stream>>>(x, flow, out, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W)); \
+        usf_launch((warp_fwd_kernel<NS, T>), dim3(blocks < res ? blocks : res), dim3(kBlock), 0, stream, x, flow, out, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W)); \
     }
     if (ns == 1 && C == 3) {  // loss-side warp of an RGB image
         const int res = resident_ctas((const void *)warp_fwd_kernel<1, T, 3>);
-        warp_fwd_kernel<1, T, 3><<<blocks < res ? blocks : res, kBlock, 0, stream>>>(
+        usf_launch((warp_fwd_kernel<1, T, 3>), dim3(blocks < res ? blocks : res), dim3(kBlock), 0, stream, 
             x, flow, out, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W));
         return note_launch(cudaGetLastError());
     }
@@ -677,7 +682,7 @@ static cudaError_t launch_bwd(int ns, int blocks, const T *x, const float *flow,
 #define USF_LAUNCH(NS)                                                                                          \
     {                                                                                                           \
         const int res = resident_ctas((const void *)warp_bwd_kernel<NS, MODE, T>);                              \
-        warp_bwd_kernel<NS, MODE, T><<<blocks < res ? blocks : res, kBlock, 0, stream>>>(                       \
+        usf_launch((warp_bwd_kernel<NS, MODE, T>), dim3(blocks < res ? blocks : res), dim3(kBlock), 0, stream,                        \
             x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W));       \
     }
     switch (ns) {
@@ -703,7 +708,7 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
     if (gx == nullptr) {
         if (ns == 1 && C == 3) {  // loss-side warp of an RGB image: gradient wrt the flow only
             const int res = resident_ctas((const void *)warp_bwd_kernel<1, 0, T, 3>);
-            warp_bwd_kernel<1, 0, T, 3><<<blocks < res ? blocks : res, kBlock, 0, stream>>>(
+            usf_launch((warp_bwd_kernel<1, 0, T, 3>), dim3(blocks < res ? blocks : res), dim3(kBlock), 0, stream, 
                 x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W));
             return note_launch(cudaGetLastError());
         }
@@ -720,7 +725,7 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
         cudaError_t e = cudaSuccess;
 #define USF_LAUNCH(NS)                                                                                       \
     if ((e = ensure_smem((const void *)warp_bwd_small<NS, T>, (int)smem)) == cudaSuccess)                    \
-        warp_bwd_small<NS, T><<<B * bpi, kBlock, smem, stream>>>(x, flow, gout, gx, gflow, C, H, W, border, rcp, \
+        usf_launch((warp_bwd_small<NS, T>), dim3(B * bpi), dim3(kBlock), smem, stream, x, flow, gout, gx, gflow, C, H, W, border, rcp, \
                                                                  make_fastdiv(W), make_fastdiv(bpi));
         switch (ns) {
             case 32: USF_LAUNCH(32); break;
@@ -740,7 +745,7 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
     if (e != cudaSuccess) { note_cuda_error(e); return USF_ERR_CUDA; }
     int st = note_launch(launch_bwd<1, T>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
     if (st != USF_OK) return st;
-#define USF_LAUNCH(NS) warp_gx_gather<NS, T><<<blocks, kBlock, 0, stream>>>(gout, gx, ws, N, C, HW, make_fastdiv(HW))
+#define USF_LAUNCH(NS) usf_launch((warp_gx_gather<NS, T>), dim3(blocks), dim3(kBlock), 0, stream, gout, gx, ws, N, C, HW, make_fastdiv(HW))
     switch (ns) {
         case 32: USF_LAUNCH(32); break;
         case 16: USF_LAUNCH(16); break;
@@ -756,7 +761,7 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
     // per SM (the list is normally empty or short), grid-stride over entries x channels
     long ovf_blocks = ((long)4 * N * C + 16L * kBlock - 1) / (16L * kBlock);
     ovf_blocks = ovf_blocks < 16 ? 16 : (ovf_blocks > 148 * 2 ? 148 * 2 : ovf_blocks);
-    warp_gx_overflow<T><<<(int)ovf_blocks, kBlock, 0, stream>>>(gout, gx, ws, 4 * N, C, HW);
+    usf_launch(warp_gx_overflow<T>, dim3((int)ovf_blocks), dim3(kBlock), 0, stream, gout, gx, ws, 4 * N, C, HW);
     return note_launch(cudaGetLastError());
 }
 
