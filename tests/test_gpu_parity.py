@@ -423,7 +423,8 @@ def test_cuda_graph_capture_of_a_step(usf):
 def test_fallback_kernels_in_a_subprocess(usf):
     """USF_DISABLE_TMA=1 + USF_DIRECT_MAX_PIXELS=0 + USF_SMALL_MAX_HW=0 force the cp.async kernels that normally
     only serve large odd-width shapes; USF_SMALL_MAX_HW=0 / USF_WARP_SMALL_MAX_HW=0 send the tiny levels to the direct corr kernels and the
-    three-kernel warp backward; USF_BWD_MIXED_TILES=0 keeps gx1 on 8x32 tiles.
+    three-kernel warp backward; USF_BWD_MIXED_TILES=0 keeps gx1 on 8x32 tiles; USF_PDL=0 launches without programmatic
+    stream serialization.
     Both must pass the same golden / oracle checks."""
     import os
     import subprocess
@@ -431,13 +432,15 @@ def test_fallback_kernels_in_a_subprocess(usf):
     here = os.path.dirname(os.path.abspath(__file__))
     for extra in ({"USF_DISABLE_TMA": "1", "USF_DIRECT_MAX_PIXELS": "0", "USF_SMALL_MAX_HW": "0"},
                   {"USF_SMALL_MAX_HW": "0", "USF_WARP_SMALL_MAX_HW": "0"},
-                  {"USF_BWD_MIXED_TILES": "0"}):
+                  {"USF_BWD_MIXED_TILES": "0"}, {"USF_PDL": "0"}):
         env = dict(os.environ, **extra)
         sel = "golden or corr_vs_oracle or nullable"
         if "USF_WARP_SMALL_MAX_HW" in extra:  # small images through the three-kernel warp backward
             sel += " or warp_vs_oracle or collapse"
         if "USF_BWD_MIXED_TILES" in extra:    # both gradients on 8x32 tiles at the full-size level
             sel = "corr_full_size or adjoint"
+        if "USF_PDL" in extra:                # plain launches instead of programmatic dependent launches
+            sel = "golden or graph_capture"
         r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu",
                             os.path.join(here, "test_gpu_parity.py"), "-k", sel],
                            env=env, capture_output=True, text=True, timeout=900)
