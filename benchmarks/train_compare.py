@@ -40,6 +40,25 @@ def stock_warp(x, flow, pad="border", mode="bilinear"):
     return F.grid_sample(x, g.permute(0, 2, 3, 1), mode=mode, padding_mode=pad, align_corners=True)
 
 
+@torch.no_grad()
+def stock_occ_backward(flow21, th=0.2):
+    """get_occu_mask_backward with stock PyTorch ops (4-tap scatter_add_ range map; utils/warp_utils.py:26-94,120-126)."""
+    b, _, h, w = flow21.shape
+    xs = torch.arange(0, w).repeat(b, h, 1)
+    ys = torch.arange(0, h).repeat(b, w, 1).transpose(1, 2)
+    v = torch.stack([xs, ys], 1).type_as(flow21) + flow21    # CPU grid + H2D per call, like the reference
+    x, y = v[:, 0].reshape(b, -1), v[:, 1].reshape(b, -1)
+    x0, y0 = torch.floor(x), torch.floor(y)
+    acc = torch.zeros(b, h * w, dtype=flow21.dtype, device=flow21.device)
+    for dx in (0, 1):
+        for dy in (0, 1):
+            xi, yi = x0 + dx, y0 + dy
+            ok = (xi >= 0) & (xi <= w - 1) & (yi >= 0) & (yi <= h - 1)
+            wgt = (1 - (x - xi).abs()) * (1 - (y - yi).abs()) * ok
+            acc.scatter_add_(1, (xi.clamp(0, w - 1) + yi.clamp(0, h - 1) * w).long(), wgt)
+    return (acc.view(b, 1, h, w).clamp(0, 1) < th).to(flow21.dtype)
+
+
 def timed(ts, steps):
     for _ in range(3):
         ts.step()
@@ -66,6 +85,7 @@ def main():
         ms, loss = timed(TrainStep(args.batch, args.height, args.width, "cuda:0", batch_directions=bd), args.steps)
         res[name] = {"ms_per_step": round(ms, 3), "pairs_per_s": round(args.batch / ms * 1e3, 1), "loss": loss}
     pw.Correlation, pw.flow_warp, fl.flow_warp = StockCorr, stock_warp, stock_warp
+    fl.get_occu_mask_backward = stock_occ_backward
     ms, loss = timed(TrainStep(args.batch, args.height, args.width, "cuda:0"), args.steps)
     res["stock_pytorch_ops"] = {"ms_per_step": round(ms, 3), "pairs_per_s": round(args.batch / ms * 1e3, 1), "loss": loss}
     res["config"] = vars(args)

@@ -16,6 +16,12 @@
  *                  norm_grid :16-23 + F.grid_sample) forward.
  *   usf_warp_bwd   autograd backward of the same (ATen grid_sampler_2d_backward
  *                  chained through norm_grid).
+ *   usf_occ_bidirection   utils/warp_utils.py:109-117 get_occu_mask_bidirection
+ *                  (flow_warp(flow21, flow12, pad="zeros") + the forward-backward
+ *                  consistency test), one kernel.
+ *   usf_occ_backward      utils/warp_utils.py:26-94,120-126 get_occu_mask_backward
+ *                  (get_corresponding_map's 4-tap forward splat + clamp + compare);
+ *                  the mask losses/flow_loss.py:99-113 uses with occ_from_back.
  *
  * Conventions (differences from the reference ABI are deliberate):
  *   - plain pointers and sizes; no at::Tensor crosses the boundary;
@@ -41,15 +47,15 @@
 extern "C" {
 #endif
 
-#define USF_ABI_VERSION 1
+#define USF_ABI_VERSION 2
 
 typedef enum usf_status {
     USF_OK = 0,
     USF_ERR_BAD_SHAPE = -1,   /* non-positive dims, H or W == 1 for warp, index > 2^31-1 */
     USF_ERR_BAD_ARG = -2,     /* null pointer, unknown dtype / pad mode / flag, md != 4 */
-    USF_ERR_WORKSPACE = -3,   /* workspace missing or smaller than usf_warp_bwd_workspace_bytes */
+    USF_ERR_WORKSPACE = -3,   /* workspace missing, misaligned or smaller than usf_*_workspace_bytes */
     USF_ERR_CUDA = -4,        /* a CUDA runtime call failed; see usf_last_cuda_error() */
-    USF_ERR_UNSUPPORTED = -5  /* valid request this build does not implement (none at ABI version 1) */
+    USF_ERR_UNSUPPORTED = -5  /* valid request this build does not implement (none at ABI version 2) */
 } usf_status;
 
 /* storage type of feature tensors; arithmetic is fp32 either way (bf16: one rounding per output element) */
@@ -125,6 +131,32 @@ size_t usf_warp_bwd_workspace_bytes(int B, int C, int H, int W, unsigned flags);
 int usf_warp_bwd(const void *x, const float *flow, const void *gout, void *gx, float *gflow, int B,
                  int C, int H, int W, int pad_mode, int dtype, unsigned flags, void *workspace,
                  size_t workspace_bytes, void *stream);
+
+/*
+ * Forward-backward consistency mask.  With w = flow_warp(flow21, flow12, pad="zeros"):
+ *   occ[b,0,y,x] = |flow12 + w|^2 > scale * (|flow12|^2 + |w|^2) + bias ? 1 : 0
+ * flow12, flow21: [B,2,H,W] fp32.  occ: [B,1,H,W] fp32 (the reference returns
+ * occ.float()).  H, W >= 2.  flags: USF_FLAG_COORD_RECIPROCAL or 0.  No gradient
+ * exists (the reference's result goes through `>`).
+ */
+int usf_occ_bidirection(const float *flow12, const float *flow21, float *occ, int B, int H, int W,
+                        float scale, float bias, unsigned flags, void *stream);
+
+/* Bytes of scratch usf_occ_backward needs (8 per pixel: the fixed-point range map).
+ * Contents need no initialisation; the pointer must be 8-byte aligned. */
+size_t usf_occ_backward_workspace_bytes(int B, int H, int W);
+
+/*
+ * Range-map occlusion mask.  Every source pixel p of flow21 splats the weight 1,
+ * split bilinearly, onto the 4 integer neighbours of p + flow21[p] that lie inside
+ * the image; occ = clamp(range, 0, 1) < th ? 1 : 0.  The sum is accumulated in
+ * 2^-40 fixed point with integer atomics, so the result is bit-identical from run
+ * to run.  Non-finite coordinates contribute nothing.
+ * flow21: [B,2,H,W] fp32.  occ: [B,1,H,W] fp32.  range_map: [B,1,H,W] fp32 or NULL
+ * (the unclamped sum, get_corresponding_map's return value).  H, W <= 2^24.
+ */
+int usf_occ_backward(const float *flow21, float *occ, float *range_map, int B, int H, int W, float th,
+                     void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,11 @@ def lib():
         L.usf_oracle_corr_bwd.argtypes = [fp, fp, fp, fp, fp, i, i, i, i, i]
         L.usf_oracle_warp_fwd.argtypes = [fp, fp, fp, i, i, i, i, i]
         L.usf_oracle_warp_bwd.argtypes = [fp, fp, fp, fp, fp, i, i, i, i, i]
+        dp = ctypes.POINTER(ctypes.c_double)
+        L.usf_oracle_occ_bidirection.argtypes = [fp, fp, fp, dp, i, i, i, ctypes.c_float, ctypes.c_float]
+        L.usf_oracle_occ_backward.argtypes = [fp, fp, fp, i, i, i, ctypes.c_float]
+        L.usf_oracle_occ_bidirection.restype = None
+        L.usf_oracle_occ_backward.restype = None
         L.usf_oracle_num_threads.restype = i
         L.usf_oracle_set_num_threads.argtypes = [i]
         for f in (L.usf_oracle_corr_fwd, L.usf_oracle_corr_bwd, L.usf_oracle_warp_fwd,
@@ -117,3 +122,31 @@ def warp_bwd(x, flow, gout, pad="border", need_gx=True, need_gflow=True):
         gflow.ctypes.data_as(ctypes.POINTER(ctypes.c_float)) if need_gflow else null,
         B, C, H, W, PAD_MODES[pad])
     return gx, gflow
+
+
+def occ_bidirection(flow12, flow21, scale=0.01, bias=0.5):
+    """utils/warp_utils.py:109-117 get_occu_mask_bidirection -> (occ [B,1,H,W], margin float64 [B,1,H,W]);
+    margin = lhs - threshold: a pixel whose |margin| is at rounding level may legitimately flip."""
+    flow12, p12 = _f32(flow12)
+    flow21, p21 = _f32(flow21)
+    B, two, H, W = flow12.shape
+    assert two == 2 and flow21.shape == flow12.shape
+    occ = np.empty((B, 1, H, W), dtype=np.float32)
+    margin = np.empty((B, 1, H, W), dtype=np.float64)
+    lib().usf_oracle_occ_bidirection(p12, p21, occ.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                     margin.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), B, H, W,
+                                     scale, bias)
+    return occ, margin
+
+
+def occ_backward(flow21, th=0.2):
+    """utils/warp_utils.py:120-126 get_occu_mask_backward -> (occ [B,1,H,W], range map [B,1,H,W] =
+    get_corresponding_map's unclamped return value, :26-94)."""
+    flow21, p21 = _f32(flow21)
+    B, two, H, W = flow21.shape
+    assert two == 2
+    occ = np.empty((B, 1, H, W), dtype=np.float32)
+    rng = np.empty((B, 1, H, W), dtype=np.float32)
+    lib().usf_oracle_occ_backward(p21, occ.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                  rng.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), B, H, W, th)
+    return occ, rng

@@ -11,6 +11,8 @@ Restates:
   pixel_grid    utils/warp_utils.py:7-13   (mesh_grid: built on the CPU, integer)
   normalise     utils/warp_utils.py:16-23  (norm_grid: 2.0*v/(size-1) - 1.0, BHW2)
   flow_warp     utils/warp_utils.py:97-106 (grid_sample, align_corners=True)
+  occ_mask_bidirection  utils/warp_utils.py:109-117
+  range_map / occ_mask_backward  utils/warp_utils.py:26-94 / :120-126
 
 Pinned against the reference's own outputs by tests/test_oracle_golden.py.
 """
@@ -67,3 +69,35 @@ def warp_fwd_bwd(x, flow, gout, pad="border", need_gx=True):
     out = flow_warp(a, f, pad=pad)
     out.backward(gout)
     return out.detach(), (a.grad if need_gx else None), f.grad
+
+
+def occ_mask_bidirection(flow12, flow21, scale=0.01, bias=0.5):
+    back = flow_warp(flow21, flow12, pad="zeros")
+    diff = flow12 + back
+    mag = (flow12 * flow12).sum(1, keepdim=True) + (back * back).sum(1, keepdim=True)
+    return ((diff * diff).sum(1, keepdim=True) > scale * mag + bias).float()
+
+
+def range_map(coords):
+    """coords: [B,2,H,W] unnormalised target positions -> [B,1,H,W] sum of bilinear splat weights."""
+    b, _, h, w = coords.shape
+    x, y = coords[:, 0].reshape(b, -1), coords[:, 1].reshape(b, -1)
+    xf, yf = torch.floor(x), torch.floor(y)
+    xc, yc = xf + 1, yf + 1
+    xf_in, yf_in = xf.clamp(0, w - 1), yf.clamp(0, h - 1)
+    xc_in, yc_in = xc.clamp(0, w - 1), yc.clamp(0, h - 1)
+    xc_out, yc_out, xf_out, yf_out = xc != xc_in, yc != yc_in, xf != xf_in, yf != yf_in
+    taps = ((xc_in, yc_in, xc_out | yc_out), (xc_in, yf_in, xc_out | yf_out),
+            (xf_in, yc_in, xf_out | yc_out), (xf_in, yf_in, xf_out | yf_out))
+    index = torch.cat([tx + ty * w for tx, ty, _ in taps], 1).long()
+    weight = torch.cat([(1 - torch.abs(x - tx)) * (1 - torch.abs(y - ty)) for tx, ty, _ in taps], 1)
+    weight[torch.cat([bad for _, _, bad in taps], 1)] = 0
+    acc = torch.zeros(b, h * w).type_as(coords)
+    acc.scatter_add_(1, index, weight)
+    return acc.view(b, h, w).unsqueeze(1)
+
+
+def occ_mask_backward(flow21, th=0.2):
+    b, _, h, w = flow21.shape
+    base = pixel_grid(b, h, w).type_as(flow21)
+    return (range_map(base + flow21).clamp(min=0.0, max=1.0) < th).float()

@@ -27,6 +27,9 @@
  *                         unnormalize, :53-57 clip, :219-246 bounds)
  *   usf_oracle_warp_bwd   autograd of the above (GridSampler.cuh:62-80 clip
  *                         gradient) chained through norm_grid.
+ *   usf_oracle_occ_bidirection / usf_oracle_occ_backward
+ *                         utils/warp_utils.py:109-117 / :26-94,120-126 (the two
+ *                         occlusion masks; see the block at the end of this file)
  *
  * Arithmetic: every coordinate operation is a separately rounded fp32 operation
  * in the reference's order (compile with -ffp-contract=off, no -ffast-math).
@@ -265,5 +268,85 @@ void usf_oracle_warp_bwd(const float *x, const float *flow, const float *gout, f
         const size_t n = (size_t)B * C * plane;
         for (size_t i = 0; i < n; ++i) gx[i] = (float)gacc[i];
         free(gacc);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Occlusion masks.
+ *
+ *   usf_oracle_occ_bidirection  utils/warp_utils.py:109-117 get_occu_mask_bidirection:
+ *       w = flow_warp(flow21, flow12, pad="zeros"); diff = flow12 + w;
+ *       mag = sum_c flow12^2 + sum_c w^2; occ = sum_c diff^2 > scale*mag + bias.
+ *       Channel sums have two terms: one rounded fp32 add each.  margin (nullable)
+ *       receives lhs - threshold in double, so a test can tell a genuine mismatch
+ *       from a pixel sitting on the threshold.
+ *   usf_oracle_occ_backward     utils/warp_utils.py:120-126 get_occu_mask_backward with
+ *       get_corresponding_map (:26-94) on mesh_grid + flow21: every source pixel adds
+ *       (1-|x-xn|)*(1-|y-yn|) to each of its four integer neighbours (xn, yn) that lie
+ *       inside the image (the reference zeroes the taps whose clamped index differs from
+ *       the unclamped one, :52-65,89); occ = clamp(range, 0, 1) < th.  The weights are
+ *       separately rounded fp32 operations as in the reference; the range map accumulates
+ *       in double (the reference's scatter_add_ sums in fp32 in source order).
+ *       Non-finite coordinates contribute nothing (undefined in the reference: .long()).
+ */
+void usf_oracle_occ_bidirection(const float *flow12, const float *flow21, float *occ, double *margin,
+                                int B, int H, int W, float scale, float bias) {
+    const size_t plane = (size_t)H * W;
+    float *warped = (float *)malloc(sizeof(float) * 2 * plane * (size_t)B);
+    usf_oracle_warp_fwd(flow21, flow12, warped, B, 2, H, W, 1 /* zeros */);
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b) {
+        for (size_t p = 0; p < plane; ++p) {
+            const float u = flow12[((size_t)b * 2) * plane + p], v = flow12[((size_t)b * 2 + 1) * plane + p];
+            const float wu = warped[((size_t)b * 2) * plane + p], wv = warped[((size_t)b * 2 + 1) * plane + p];
+            volatile float d0 = u + wu, d1 = v + wv;
+            volatile float uu = u * u, vv = v * v, m12 = uu + vv;
+            volatile float w0 = wu * wu, w1 = wv * wv, mw = w0 + w1;
+            volatile float mag = m12 + mw;
+            volatile float sm = scale * mag;
+            volatile float thresh = sm + bias;
+            volatile float q0 = d0 * d0, q1 = d1 * d1, lhs = q0 + q1;
+            occ[(size_t)b * plane + p] = lhs > thresh ? 1.0f : 0.0f;
+            if (margin) margin[(size_t)b * plane + p] = (double)lhs - (double)thresh;
+        }
+    }
+    free(warped);
+}
+
+/* One neighbour of get_corresponding_map: weight (1-|x-xn|)*(1-|y-yn|), zero when outside. */
+static inline void splat_tap(double *acc, float x, float y, float xn, float yn, int H, int W) {
+    if (!(xn >= 0.0f && xn <= (float)(W - 1) && yn >= 0.0f && yn <= (float)(H - 1))) return;
+    volatile float ax = x - xn, ay = y - yn;
+    volatile float wx = 1.0f - fabsf(ax), wy = 1.0f - fabsf(ay);
+    volatile float w = wx * wy;
+    acc[(size_t)yn * W + (size_t)xn] += (double)w;
+}
+
+void usf_oracle_occ_backward(const float *flow21, float *occ, float *range_map, int B, int H, int W,
+                             float th) {
+    const size_t plane = (size_t)H * W;
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b) {
+        double *acc = (double *)calloc(plane, sizeof(double));
+        for (int yo = 0; yo < H; ++yo) {
+            for (int xo = 0; xo < W; ++xo) {
+                volatile float x = (float)xo + flow21[IDX4(b, 0, yo, xo, 2, H, W)];
+                volatile float y = (float)yo + flow21[IDX4(b, 1, yo, xo, 2, H, W)];
+                if (!isfinite(x) || !isfinite(y)) continue;
+                const float x1 = floorf(x), y1 = floorf(y);
+                volatile float x0 = x1 + 1.0f, y0 = y1 + 1.0f;
+                splat_tap(acc, x, y, x0, y0, H, W); /* ceil, ceil */
+                splat_tap(acc, x, y, x0, y1, H, W); /* ceil x, floor y */
+                splat_tap(acc, x, y, x1, y0, H, W); /* floor x, ceil y */
+                splat_tap(acc, x, y, x1, y1, H, W); /* floor, floor */
+            }
+        }
+        for (size_t p = 0; p < plane; ++p) {
+            const float r = (float)acc[p];
+            if (range_map) range_map[(size_t)b * plane + p] = r;
+            const float c = r < 0.0f ? 0.0f : (r > 1.0f ? 1.0f : r);
+            occ[(size_t)b * plane + p] = c < th ? 1.0f : 0.0f;
+        }
+        free(acc);
     }
 }

@@ -47,3 +47,8 @@ def corr_golden():
 @pytest.fixture(scope="session")
 def warp_golden():
     return _load("warp_golden.npz")
+
+
+@pytest.fixture(scope="session")
+def occ_golden():
+    return _load("occ_golden.npz")

@@ -27,14 +27,14 @@ def declared_symbols():
 def test_header_symbols_are_exported(lib):
     from unsamflow_b200 import _lib
     names = declared_symbols()
-    assert len(names) == 10
+    assert len(names) == 13
     assert sorted(_lib.SYMBOLS) == names
     for n in names:
         assert getattr(lib, n) is not None
 
 
 def test_abi_version_and_status_strings(lib):
-    assert lib.usf_abi_version() == 1
+    assert lib.usf_abi_version() == 2
     for st in (0, -1, -2, -3, -4, -5):
         assert lib.usf_status_string(st)
     assert b"unknown" in lib.usf_status_string(-99)
@@ -69,6 +69,17 @@ def test_argument_validation_without_a_gpu(lib):
     # ... smaller ones run as one kernel with shared-memory tap lists: no workspace
     assert lib.usf_warp_bwd_workspace_bytes(8, 96, 16, 52, 0) == 0
     assert lib.usf_warp_bwd_workspace_bytes(1, 1, 32, 32, 0) == 0
+    # occlusion masks: null pointers, unknown flag, H/W >= 2 for the warp inside, workspace size / alignment
+    assert lib.usf_occ_bidirection(p, None, p, 1, 2, 2, 0.01, 0.5, 0, None) == BAD_ARG
+    assert lib.usf_occ_bidirection(p, p, p, 1, 2, 2, 0.01, 0.5, 4, None) == BAD_ARG
+    assert lib.usf_occ_bidirection(p, p, p, 1, 1, 2, 0.01, 0.5, 0, None) == BAD_SHAPE
+    assert lib.usf_occ_backward_workspace_bytes(8, 256, 832) == 8 * 256 * 832 * 8
+    assert lib.usf_occ_backward_workspace_bytes(0, 4, 4) == 0
+    assert lib.usf_occ_backward(None, p, None, 1, 2, 2, 0.2, p, 32, None) == BAD_ARG
+    assert lib.usf_occ_backward(p, p, None, 1, 0, 2, 0.2, p, 32, None) == BAD_SHAPE
+    assert lib.usf_occ_backward(p, p, None, 1, 2, 2, 0.2, None, 0, None) == WORKSPACE
+    assert lib.usf_occ_backward(p, p, None, 1, 2, 2, 0.2, p, 31, None) == WORKSPACE
+    assert lib.usf_occ_backward(p, p, None, 1, 2, 2, 0.2, ctypes.c_void_p(p.value + 4), 32, None) == WORKSPACE
 
 
 def test_launch_counter_is_per_thread_and_resettable(lib):

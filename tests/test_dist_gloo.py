@@ -74,6 +74,7 @@ def _ddp_worker(rank, world, port, q):
             return torch_port.cost_volume(a, b)
 
     pw.Correlation, pw.flow_warp, fl.flow_warp = PortCorr, torch_port.flow_warp, torch_port.flow_warp
+    fl.get_occu_mask_backward = torch_port.occ_mask_backward
     from unsamflow_b200.train_step import TrainStep
     torch.set_num_threads(2)
     dist_util.init_from_env("gloo")

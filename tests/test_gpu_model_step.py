@@ -50,8 +50,12 @@ class PortCorrelation(torch.nn.Module):
 def run_step(corr_cls, model_warp, loss_warp, batch_directions=False):
     import unsamflow_b200.flow_loss as fl
     import unsamflow_b200.pwclite as pw
-    saved = (pw.Correlation, pw.flow_warp, fl.flow_warp)
+    from oracle import torch_port
+    saved = (pw.Correlation, pw.flow_warp, fl.flow_warp, fl.get_occu_mask_backward)
     pw.Correlation, pw.flow_warp, fl.flow_warp = corr_cls, model_warp, loss_warp
+    # the visibility masks are a hard threshold: both arms take the SAME (ported) mask code so that the
+    # comparison isolates the correlation / warp ops; the mask kernels have their own parity tests
+    fl.get_occu_mask_backward = torch_port.occ_mask_backward
     try:
         torch.manual_seed(5)
         model = pw.PWCLite(batch_directions=batch_directions).cuda()
@@ -65,7 +69,7 @@ def run_step(corr_cls, model_warp, loss_warp, batch_directions=False):
         loss.backward()
         return loss.item(), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}
     finally:
-        pw.Correlation, pw.flow_warp, fl.flow_warp = saved
+        pw.Correlation, pw.flow_warp, fl.flow_warp, fl.get_occu_mask_backward = saved
 
 
 @pytest.fixture()

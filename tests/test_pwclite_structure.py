@@ -27,6 +27,7 @@ def cpu_ops(monkeypatch):
     monkeypatch.setattr(pwclite_mod, "Correlation", _PortCorr)
     monkeypatch.setattr(pwclite_mod, "flow_warp", torch_port.flow_warp)
     monkeypatch.setattr(flow_loss_mod, "flow_warp", torch_port.flow_warp)
+    monkeypatch.setattr(flow_loss_mod, "get_occu_mask_backward", torch_port.occ_mask_backward)
 
 
 def test_parameter_count_and_output_shapes(cpu_ops):

@@ -30,6 +30,9 @@ int corr_bwd_small_f32(const float *, const float *, const float *, float *, flo
                        cudaStream_t);
 int corr_fwd_small_bf16(const void *, const void *, void *, int, int, int, int, unsigned, float, cudaStream_t);
 int corr_bwd_small_bf16(const void *, const void *, const void *, void *, void *, int, int, int, int, cudaStream_t);
+int occ_bidirection(const float *, const float *, float *, int, int, int, float, float, unsigned, cudaStream_t);
+size_t occ_backward_workspace_bytes(int B, int H, int W);
+int occ_backward(const float *, float *, float *, int, int, int, float, void *, cudaStream_t);
 bool corr_small_applies(int H, int W);  // whole image <= 256 pixels: corr_small.cu
 
 long kDirectMaxPixels = [] {
@@ -99,7 +102,7 @@ const char *usf_status_string(int status) {
         case USF_OK: return "ok";
         case USF_ERR_BAD_SHAPE: return "bad shape (non-positive dim, H or W < 2 for warp, or > 2^31-1 elements)";
         case USF_ERR_BAD_ARG: return "bad argument (null pointer, unknown dtype/pad/flag, or max_disp != 4)";
-        case USF_ERR_WORKSPACE: return "workspace missing or too small (see usf_warp_bwd_workspace_bytes)";
+        case USF_ERR_WORKSPACE: return "workspace missing, misaligned or too small (see usf_*_workspace_bytes)";
         case USF_ERR_CUDA: return "CUDA call failed (see usf_last_cuda_error)";
         case USF_ERR_UNSUPPORTED: return "not implemented in this build";
         default: return "unknown status";
@@ -198,6 +201,30 @@ int usf_warp_bwd(const void *x, const float *flow, const void *gout, void *gx, f
         return warp_bwd_bf16(x, flow, gout, gx, gflow, B, C, H, W, pad_mode, flags, workspace, workspace_bytes,
                              (cudaStream_t)stream);
     return USF_ERR_BAD_ARG;
+}
+
+int usf_occ_bidirection(const float *flow12, const float *flow21, float *occ, int B, int H, int W, float scale,
+                        float bias, unsigned flags, void *stream) {
+    if (!flow12 || !flow21 || !occ) return USF_ERR_BAD_ARG;
+    if (flags & ~USF_FLAG_COORD_RECIPROCAL) return USF_ERR_BAD_ARG;
+    if (int st = check_dims(B, 2, H, W, 2)) return st;
+    if (H < 2 || W < 2) return USF_ERR_BAD_SHAPE;  // flow_warp divides by (size-1): utils/warp_utils.py:21-22
+    return occ_bidirection(flow12, flow21, occ, B, H, W, scale, bias, flags, (cudaStream_t)stream);
+}
+
+size_t usf_occ_backward_workspace_bytes(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return occ_backward_workspace_bytes(B, H, W);
+}
+
+int usf_occ_backward(const float *flow21, float *occ, float *range_map, int B, int H, int W, float th,
+                     void *workspace, size_t workspace_bytes, void *stream) {
+    if (!flow21 || !occ) return USF_ERR_BAD_ARG;
+    if (int st = check_dims(B, 2, H, W, 2)) return st;
+    if (H > (1 << 24) || W > (1 << 24)) return USF_ERR_BAD_SHAPE;  // pixel coordinates must be exact in fp32
+    if (!workspace || workspace_bytes < occ_backward_workspace_bytes(B, H, W) || ((uintptr_t)workspace & 7))
+        return USF_ERR_WORKSPACE;
+    return occ_backward(flow21, occ, range_map, B, H, W, th, workspace, (cudaStream_t)stream);
 }
 
 }  // extern "C"

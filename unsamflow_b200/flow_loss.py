@@ -8,12 +8,19 @@ this repo accelerates are
     im1_recons = flow_warp(im2_scaled, flow[:, :2], pad=warp_pad)     losses/flow_loss.py:130
     im2_recons = flow_warp(im1_scaled, flow[:, 2:], pad=warp_pad)     losses/flow_loss.py:131
 
-Everything else (area resize, SSIM, masks) is elementwise PyTorch as in the reference and out of scope.
+and, with occ_from_back, the two range-map occlusion masks
+
+    occu_mask1 = 1 - get_occu_mask_backward(flow[:, 2:], th=0.2)      losses/flow_loss.py:101
+    occu_mask2 = 1 - get_occu_mask_backward(flow[:, :2], th=0.2)      losses/flow_loss.py:102
+
+(unsamflow_b200/occlusion.py).  Everything else (area resize, SSIM) is elementwise PyTorch as in the
+reference and out of scope.
 """
 import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .occlusion import get_occu_mask_backward
 from .warp import flow_warp
 
 
@@ -27,28 +34,6 @@ def ssim_distance(x, y):
     sig_xy = pool(x * y) - mu_x * mu_y
     ssim = ((2 * mu_x * mu_y + c1) * (2 * sig_xy + c2)) / ((mu_x * mu_x + mu_y * mu_y + c1) * (sig_x + sig_y + c2))
     return torch.clamp((1 - ssim) / 2, 0, 1)
-
-
-@torch.no_grad()
-def occlusion_from_backward_flow(flow21, th=0.2):
-    """Forward-splat range map of flow21; pixels nobody maps to are occluded
-    (utils/warp_utils.py:26-94, :120-126).  Built on the device (the reference builds the pixel grid on
-    the CPU every call)."""
-    b, _, h, w = flow21.shape
-    ys, xs = torch.meshgrid(torch.arange(h, device=flow21.device, dtype=flow21.dtype),
-                            torch.arange(w, device=flow21.device, dtype=flow21.dtype), indexing="ij")
-    x = (xs + flow21[:, 0]).reshape(b, -1)
-    y = (ys + flow21[:, 1]).reshape(b, -1)
-    x0, y0 = torch.floor(x), torch.floor(y)
-    acc = torch.zeros(b, h * w, dtype=flow21.dtype, device=flow21.device)
-    for dx in (0, 1):
-        for dy in (0, 1):
-            xi, yi = x0 + dx, y0 + dy
-            ok = (xi >= 0) & (xi <= w - 1) & (yi >= 0) & (yi <= h - 1)
-            wgt = (1 - (x - xi).abs()) * (1 - (y - yi).abs()) * ok
-            idx = (xi.clamp(0, w - 1) + yi.clamp(0, h - 1) * w).long()
-            acc.scatter_add_(1, idx, wgt)
-    return (acc.view(b, 1, h, w).clamp(0, 1) < th).to(flow21.dtype)
 
 
 class UnFlowLoss(nn.Module):
@@ -68,8 +53,9 @@ class UnFlowLoss(nn.Module):
         """pyramid_flows: list of [B,4,h,w] = cat(flow12, flow21) per scale, finest first
         (trainer/kitti_trainer_ar.py:115-127)."""
         top = pyramid_flows[0]
-        vis1 = 1 - occlusion_from_backward_flow(top[:, 2:])
-        vis2 = 1 - occlusion_from_backward_flow(top[:, :2])
+        # occ_from_back (losses/flow_loss.py:99-106): range-map masks of the finest flows, no gradient
+        vis1 = 1 - get_occu_mask_backward(top[:, 2:].detach())
+        vis2 = 1 - get_occu_mask_backward(top[:, :2].detach())
         total = 0.0
         for i, flow in enumerate(pyramid_flows):
             if self.w_scales[i] <= 0:

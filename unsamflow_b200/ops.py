@@ -184,6 +184,61 @@ def warp_bwd(x, flow, gout, pad="border", need_gx=True, need_gflow=True, recipro
     return gx, gflow
 
 
+def _flow_pair(t, name):
+    if not isinstance(t, torch.Tensor) or t.dim() != 4 or t.shape[1] != 2:
+        raise ValueError(f"{name}: expected a 4-D flow tensor [B,2,H,W]")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: unsamflow_b200 runs on CUDA tensors only (got {t.device}); "
+                           "there is no CPU path")
+    return t.detach().float().contiguous()
+
+
+def occ_bidirection(flow12, flow21, scale=0.01, bias=0.5, reciprocal=False, out=None):
+    """[B,2,H,W] x2 -> [B,1,H,W] fp32 mask (1 = occluded); utils/warp_utils.py:109-117 in one kernel."""
+    L = _lib.load()
+    flow12, flow21 = _flow_pair(flow12, "flow12"), _flow_pair(flow21, "flow21")
+    _same(flow12, flow21, "flow12", "flow21")
+    B, _, H, W = flow12.shape
+    if H < 2 or W < 2:
+        raise ValueError("get_occu_mask_bidirection needs H, W >= 2 (flow_warp divides by size-1)")
+    if out is None:
+        out = torch.empty((B, 1, H, W), dtype=torch.float32, device=flow12.device)
+    if flow12.numel() == 0:
+        return out
+    with torch.cuda.device(flow12.device):
+        st = L.usf_occ_bidirection(flow12.data_ptr(), flow21.data_ptr(), out.data_ptr(), B, H, W, float(scale),
+                                   float(bias), _flags(reciprocal=reciprocal), _stream(flow12))
+    _lib.check(st, "usf_occ_bidirection")
+    return out
+
+
+def occ_backward_workspace_bytes(flow21):
+    B, _, H, W = flow21.shape
+    return int(_lib.load().usf_occ_backward_workspace_bytes(B, H, W))
+
+
+def occ_backward(flow21, th=0.2, want_range_map=False, out=None, workspace=None):
+    """[B,2,H,W] -> [B,1,H,W] fp32 mask (1 = no source pixel maps here); utils/warp_utils.py:120-126.
+    want_range_map=True returns (mask, range map) -- get_corresponding_map's value (:26-94)."""
+    L = _lib.load()
+    flow21 = _flow_pair(flow21, "flow21")
+    B, _, H, W = flow21.shape
+    if out is None:
+        out = torch.empty((B, 1, H, W), dtype=torch.float32, device=flow21.device)
+    rng = torch.empty_like(out) if want_range_map else None
+    if flow21.numel() == 0:
+        return (out, rng) if want_range_map else out
+    ws_bytes = L.usf_occ_backward_workspace_bytes(B, H, W)
+    ws = workspace if workspace is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=flow21.device)
+    if ws.numel() * ws.element_size() < ws_bytes:
+        raise ValueError(f"workspace has {ws.numel() * ws.element_size()} bytes, need {ws_bytes}")
+    with torch.cuda.device(flow21.device):
+        st = L.usf_occ_backward(flow21.data_ptr(), out.data_ptr(), rng.data_ptr() if want_range_map else None,
+                                B, H, W, float(th), ws.data_ptr(), ws_bytes, _stream(flow21))
+    _lib.check(st, "usf_occ_backward")
+    return (out, rng) if want_range_map else out
+
+
 def launch_count():
     return int(_lib.load().usf_launch_count())
 
