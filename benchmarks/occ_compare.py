@@ -59,7 +59,9 @@ def main():
     ws = torch.empty(ops.occ_backward_workspace_bytes(flow21), dtype=torch.uint8, device="cuda")
     flush = torch.zeros(64 * 1024 * 1024, device="cuda")
     n = B * H * W
-    res = {"config": vars(args), "gpu": torch.cuda.get_device_name(0)}
+    res = {"config": vars(args), "gpu": torch.cuda.get_device_name(0),
+           "splat_lane_merge": os.environ.get("USF_OCC_MERGE", "1") != "0",
+           "splat_pixels_per_thread": os.environ.get("USF_OCC_ITER", "default")}
     for name, usf_fn, stock_fn, bytes_px in (
         ("occ_backward", lambda: ops.occ_backward(flow21, out=out, workspace=ws), lambda: stock_occ_backward(flow21), 12),
         ("occ_bidirection", lambda: ops.occ_bidirection(flow12, flow21, out=out), lambda: stock_occ_bidirection(flow12, flow21), 20),

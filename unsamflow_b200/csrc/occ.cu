@@ -14,6 +14,8 @@
 // order the taps arrive in, which a float-atomic scatter (what the reference does on a GPU) cannot promise.  Each
 // weight is the reference's own fp32 product, quantised with an error below 2^-41; the sum is then exact, i.e. it
 // sits inside the fp32 summation noise of the reference's sequential scatter_add_ (~1e-7).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "warp_coord.cuh"
 
@@ -80,28 +82,80 @@ __device__ __forceinline__ Axis splat_axis(int i, float fl, int size) {
     return a;
 }
 
-__device__ __forceinline__ void splat_add(unsigned long long *plane, int off, bool ok, float w) {
-    if (ok && w > 0.f) atomicAdd(plane + off, __float2ull_rn(__fmul_rn(w, kFixScale)));
+__device__ __forceinline__ unsigned long long splat_fix(bool ok, float w) {
+    return (ok && w > 0.f) ? __float2ull_rn(__fmul_rn(w, kFixScale)) : 0ull;
 }
 
+// MERGE: the x-neighbouring lane of a smooth flow lands in the next cell of the same row, so its (floor x) taps
+// are this lane's (ceil x) taps.  The receiving lane (i+1) folds lane i's two ceil-x weights into its own floor-x
+// weights before the atomic: two REDs per pixel instead of four.  The fold is an INTEGER add of the same
+// fixed-point terms, so the result is bit-identical to the unmerged kernel (USF_OCC_MERGE=0).  Only target
+// coordinates are compared, never source adjacency, so row ends and image boundaries need no special case beyond
+// the image index; a non-zero folded term implies the giver's tap was inside the image, which makes the
+// receiver's address (the same coordinates) valid even when its own taps are not.
+// ITER pixels per thread, kBlock apart (lanes stay x-neighbours in every round): all 2*ITER flow loads are issued
+// before the first is consumed, and the grid shrinks ITER-fold -- with one pixel per thread the kernel is a chain
+// of load latency -> atomics -> exit per warp and spends its time launching CTAs (ncu: 26 us for 1.7 M pixels at
+// 12 % of DRAM bandwidth).
+template <bool MERGE, int ITER>
 __global__ void __launch_bounds__(kBlock)
 occ_splat_kernel(const float *__restrict__ flow21, unsigned long long *__restrict__ acc, int N, int H, int W,
                  FastDiv dHW, FastDiv dW) {
     pdl_wait();
-    const int p = blockIdx.x * kBlock + threadIdx.x;
-    if (p >= N) return;
     const int HW = H * W;
-    const int b = dHW.div(p), rem = p - b * HW;
-    const int y = dW.div(rem), xo = rem - y * W;
-    const float *f = flow21 + (size_t)b * 2 * HW;
-    const Axis ax = splat_axis(xo, __ldg(f + rem), W);
-    const Axis ay = splat_axis(y, __ldg(f + HW + rem), H);
-    unsigned long long *plane = acc + (size_t)b * HW;
-    const int o = ay.lo * W + ax.lo;
-    splat_add(plane, o + W + 1, ax.hi_ok && ay.hi_ok, __fmul_rn(ax.w_hi, ay.w_hi));  // ceil, ceil
-    splat_add(plane, o + 1, ax.hi_ok && ay.lo_ok, __fmul_rn(ax.w_hi, ay.w_lo));      // ceil x, floor y
-    splat_add(plane, o + W, ax.lo_ok && ay.hi_ok, __fmul_rn(ax.w_lo, ay.w_hi));      // floor x, ceil y
-    splat_add(plane, o, ax.lo_ok && ay.lo_ok, __fmul_rn(ax.w_lo, ay.w_lo));          // floor, floor
+    const int base = blockIdx.x * (kBlock * ITER) + threadIdx.x;
+    float u[ITER], v[ITER];
+    int bi[ITER], ri[ITER];
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        const int p = base + it * kBlock;
+        u[it] = v[it] = 0.f;
+        bi[it] = -1;
+        ri[it] = 0;
+        if (p < N) {
+            bi[it] = dHW.div(p);
+            ri[it] = p - bi[it] * HW;
+            const float *f = flow21 + (size_t)bi[it] * 2 * HW;
+            u[it] = __ldg(f + ri[it]);
+            v[it] = __ldg(f + HW + ri[it]);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < ITER; ++it) {
+        const int b = bi[it];
+        const bool live = b >= 0;
+        int xlo = -1, ylo = -1;
+        unsigned long long t_ll = 0, t_hl = 0, t_lh = 0, t_hh = 0;  // (x lo|hi, y lo|hi) in 2^-40 units
+        if (live) {
+            const int y = dW.div(ri[it]), xo = ri[it] - y * W;
+            const Axis ax = splat_axis(xo, u[it], W);
+            const Axis ay = splat_axis(y, v[it], H);
+            xlo = ax.lo;
+            ylo = ay.lo;
+            t_hh = splat_fix(ax.hi_ok && ay.hi_ok, __fmul_rn(ax.w_hi, ay.w_hi));  // ceil, ceil
+            t_hl = splat_fix(ax.hi_ok && ay.lo_ok, __fmul_rn(ax.w_hi, ay.w_lo));  // ceil x, floor y
+            t_lh = splat_fix(ax.lo_ok && ay.hi_ok, __fmul_rn(ax.w_lo, ay.w_hi));  // floor x, ceil y
+            t_ll = splat_fix(ax.lo_ok && ay.lo_ok, __fmul_rn(ax.w_lo, ay.w_lo));  // floor, floor
+        }
+        if (MERGE) {  // every lane of the warp is here in every round (no early exit)
+            const unsigned full = 0xffffffffu;
+            const int lane = threadIdx.x & 31;
+            const int pb = __shfl_up_sync(full, b, 1), px = __shfl_up_sync(full, xlo, 1), py = __shfl_up_sync(full, ylo, 1);
+            const unsigned long long p_hl = __shfl_up_sync(full, t_hl, 1), p_hh = __shfl_up_sync(full, t_hh, 1);
+            const bool take = lane > 0 && live && pb == b && px + 1 == xlo && py == ylo;
+            const bool given = __shfl_down_sync(full, take ? 1 : 0, 1) != 0 && lane < 31;
+            if (take) { t_ll += p_hl; t_lh += p_hh; }
+            if (given) { t_hl = 0; t_hh = 0; }
+        }
+        if (live) {
+            unsigned long long *plane = acc + (size_t)b * HW;
+            const int o = ylo * W + xlo;
+            if (t_ll) atomicAdd(plane + o, t_ll);
+            if (t_hl) atomicAdd(plane + o + 1, t_hl);
+            if (t_lh) atomicAdd(plane + o + W, t_lh);
+            if (t_hh) atomicAdd(plane + o + W + 1, t_hh);
+        }
+    }
 }
 
 // occ = clamp(range, 0, 1) < th (warp_utils.py:124-126); the range map itself is written too when asked for.
@@ -136,8 +190,23 @@ int occ_backward(const float *flow21, float *occ, float *range_map, int B, int H
     unsigned long long *acc = (unsigned long long *)workspace;
     cudaError_t e = cudaMemsetAsync(acc, 0, (size_t)N * sizeof(unsigned long long), stream);
     if (e != cudaSuccess) { note_cuda_error(e); return USF_ERR_CUDA; }
-    int st = note_launch(usf_launch(occ_splat_kernel, dim3(blocks), dim3(kBlock), 0, stream, flow21, acc, N, H, W,
-                                    make_fastdiv(H * W), make_fastdiv(W)));
+    static const bool merge = [] {
+        const char *e = getenv("USF_OCC_MERGE");
+        return !(e && e[0] == '0');
+    }();
+    static const int iter = [] {  // pixels per thread of the splat: 1 or 4 (A/B switch)
+        const char *e = getenv("USF_OCC_ITER");
+        return (e && e[0] == '4') ? 4 : 1;
+    }();
+    const int sblocks = (N + kBlock * iter - 1) / (kBlock * iter);
+    cudaError_t le;
+#define USF_SPLAT(M, I) \
+    le = usf_launch(occ_splat_kernel<M, I>, dim3(sblocks), dim3(kBlock), 0, stream, flow21, acc, N, H, W, \
+                    make_fastdiv(H * W), make_fastdiv(W))
+    if (iter == 4) { if (merge) USF_SPLAT(true, 4); else USF_SPLAT(false, 4); }
+    else { if (merge) USF_SPLAT(true, 1); else USF_SPLAT(false, 1); }
+#undef USF_SPLAT
+    int st = note_launch(le);
     if (st != USF_OK) return st;
     return note_launch(usf_launch(occ_threshold_kernel, dim3(blocks), dim3(kBlock), 0, stream,
                                   (const unsigned long long *)acc, occ, range_map, N, th));
