@@ -50,6 +50,7 @@ def main():
     ap.add_argument("--height", type=int, default=256)
     ap.add_argument("--width", type=int, default=832)
     ap.add_argument("--iters", type=int, default=50)
+    ap.add_argument("--skip-stock", action="store_true", help="time only the usf kernels")
     args = ap.parse_args()
     B, H, W = args.batch, args.height, args.width
     coarse = 6.0 * torch.randn(B, 2, H // 16, W // 16, device="cuda")
@@ -61,7 +62,8 @@ def main():
     n = B * H * W
     res = {"config": vars(args), "gpu": torch.cuda.get_device_name(0),
            "splat_lane_merge": os.environ.get("USF_OCC_MERGE", "1") != "0",
-           "splat_pixels_per_thread": os.environ.get("USF_OCC_ITER", "default")}
+           "splat_pixels_per_thread": os.environ.get("USF_OCC_ITER", "default"),
+           "splat_tile_window": os.environ.get("USF_OCC_TILE", "0") == "1"}
     for name, usf_fn, stock_fn, bytes_px in (
         ("occ_backward", lambda: ops.occ_backward(flow21, out=out, workspace=ws), lambda: stock_occ_backward(flow21), 12),
         ("occ_bidirection", lambda: ops.occ_bidirection(flow12, flow21, out=out), lambda: stock_occ_bidirection(flow12, flow21), 20),
@@ -70,7 +72,7 @@ def main():
         usf_fn()
         launches = ops.launch_count()
         warm, cold = timed(usf_fn, args.iters, None), timed(usf_fn, args.iters, flush)
-        stock = timed(stock_fn, max(args.iters // 5, 5), None)
+        stock = float("nan") if args.skip_stock else timed(stock_fn, max(args.iters // 5, 5), None)
         res[name] = {"usf_us_warm": round(warm, 2), "usf_us_cold_l2": round(cold, 2), "stock_pytorch_us": round(stock, 1),
                      "speedup_warm": round(stock / warm, 1), "kernels": launches,
                      "algorithmic_gbs_warm": round(n * bytes_px / warm / 1e3, 1),

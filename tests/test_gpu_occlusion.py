@@ -248,16 +248,27 @@ def test_drop_in_signatures_and_errors(ops):
     assert torch.isfinite(loss) and torch.isfinite(flow21.grad).all()
 
 
-def test_splat_variants_in_subprocesses_are_bit_identical(ops, tmp_path):
+SPLAT_VARIANTS = {
+    "unmerged": ({"USF_OCC_MERGE": "0", "USF_OCC_ITER": "1"}, True),
+    "iter4": ({"USF_OCC_ITER": "4"}, True),
+    "iter4_unmerged": ({"USF_OCC_MERGE": "0", "USF_OCC_ITER": "4"}, False),
+    "tile_window": ({"USF_OCC_TILE": "1"}, True),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(SPLAT_VARIANTS))
+def test_splat_variants_in_subprocesses_are_bit_identical(ops, tmp_path, variant):
     """USF_OCC_MERGE=0 issues all four atomics per pixel instead of folding x-neighbouring lanes first;
-    USF_OCC_ITER selects 1 or 4 pixels per thread.  The fold is an integer add of the same terms and the
-    accumulation is integer: every variant must give the same bits as the default, and pass the same golden /
-    property checks."""
+    USF_OCC_ITER selects 1 or 4 pixels per thread; USF_OCC_TILE=1 accumulates per source tile in a shared-memory
+    window first.  Every add is an integer add of the same fixed-point terms: each variant must give the same
+    bits as the default, and pass the same golden / property checks."""
     import os
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
-    flows = {"smooth": smooth_flow(4, 128, 416, 5.0, 61),
+    wild = smooth_flow(1, 70, 150, 4.0, 63)
+    wild[:, :, 20:40, 30:90] *= 9.0   # a region whose taps leave the tile window
+    flows = {"smooth": smooth_flow(4, 128, 416, 5.0, 61), "wild_patch": wild.contiguous(),
              "rough": 3.0 * torch.randn(2, 2, 61, 37, generator=torch.Generator().manual_seed(62))}
     torch.save(flows, tmp_path / "flows.pt")
     mine = {k: ops.occ_backward(v.cuda(), want_range_map=True)[1].cpu() for k, v in flows.items()}
@@ -265,16 +276,15 @@ def test_splat_variants_in_subprocesses_are_bit_identical(ops, tmp_path):
               "f = torch.load(%r); "
               "torch.save({k: ops.occ_backward(v.cuda(), want_range_map=True)[1].cpu() for k, v in f.items()}, %r)"
               % (os.path.dirname(here), str(tmp_path / "flows.pt"), str(tmp_path / "other.pt")))
-    for extra, rerun in (({"USF_OCC_MERGE": "0", "USF_OCC_ITER": "1"}, True), ({"USF_OCC_ITER": "4"}, True),
-                         ({"USF_OCC_MERGE": "0", "USF_OCC_ITER": "4"}, False), ({"USF_OCC_ITER": "1"}, False)):
-        env = dict(os.environ, **extra)
-        if rerun:
-            r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__),
-                                "-k", "golden or collapse or non_finite or properties"],
-                               env=env, capture_output=True, text=True, timeout=600)
-            assert r.returncode == 0, str(extra) + r.stdout[-3000:] + r.stderr[-2000:]
-        r = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, str(extra) + r.stdout[-2000:] + r.stderr[-2000:]
-        other = torch.load(tmp_path / "other.pt")
-        for k in flows:
-            assert torch.equal(mine[k], other[k]), (extra, k)
+    extra, rerun = SPLAT_VARIANTS[variant]
+    env = dict(os.environ, **extra)
+    if rerun:
+        r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.abspath(__file__),
+                            "-k", "golden or collapse or non_finite or properties"],
+                           env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, str(extra) + r.stdout[-3000:] + r.stderr[-2000:]
+    r = subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, str(extra) + r.stdout[-2000:] + r.stderr[-2000:]
+    other = torch.load(tmp_path / "other.pt")
+    for k in flows:
+        assert torch.equal(mine[k], other[k]), (extra, k)

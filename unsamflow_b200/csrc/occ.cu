@@ -158,6 +158,88 @@ occ_splat_kernel(const float *__restrict__ flow21, unsigned long long *__restric
     }
 }
 
+// USF_OCC_TILE=1 (opt-in): one CTA per 16x64 tile of SOURCE pixels.  Taps are accumulated with shared-memory
+// integer atomics in a window of 33x81 targets placed where the tile's centre pixel lands (+-8 pixels of slack
+// around the displaced tile), and the window is flushed with one RED per touched target, consecutive lanes on
+// consecutive targets: ~1 coalesced global RED per pixel instead of 4 scattered ones (the default kernel is bound
+// by the number of RED sectors).  Taps that fall outside the window take the global path.  All
+// adds are integer adds of the same fixed-point terms: bit-identical to the other variants.
+constexpr int kTH = 16, kTW = 64, kR = 8;
+constexpr int kWH = kTH + 2 * kR + 1, kWW = kTW + 2 * kR + 1;
+
+__global__ void __launch_bounds__(kBlock)
+occ_splat_tile_kernel(const float *__restrict__ flow21, unsigned long long *__restrict__ acc, int H, int W,
+                      int tiles_x, int tiles_y) {
+    __shared__ unsigned long long win[kWH * kWW];
+    __shared__ int org[2];
+    pdl_wait();
+    const int HW = H * W;
+    int t = blockIdx.x;
+    const int tx0 = (t % tiles_x) * kTW;
+    t /= tiles_x;
+    const int ty0 = (t % tiles_y) * kTH;
+    const int b = t / tiles_y;
+    const float *f = flow21 + (size_t)b * 2 * HW;
+    if (threadIdx.x == 0) {
+        const int cx = min(tx0 + kTW / 2, W - 1), cy = min(ty0 + kTH / 2, H - 1);
+        const float cu = __ldg(f + cy * W + cx), cv = __ldg(f + HW + cy * W + cx);
+        // non-finite or huge centre flow: any window position is correct (it only decides which taps go global)
+        const int ou = (fabsf(cu) < 1048576.f) ? __float2int_rn(cu) : 0;
+        const int ov = (fabsf(cv) < 1048576.f) ? __float2int_rn(cv) : 0;
+        org[0] = tx0 + ou - kR;
+        org[1] = ty0 + ov - kR;
+    }
+    for (int i = threadIdx.x; i < kWH * kWW; i += kBlock) win[i] = 0ull;
+    const int lx = threadIdx.x % kTW, ly = threadIdx.x / kTW;  // 64 columns x 4 rows of threads, 4 rows each
+    constexpr int RPT = kTH / (kBlock / kTW);
+    const int xo = tx0 + lx;
+    float u[RPT], v[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const int y = ty0 + ly + k * (kBlock / kTW);
+        u[k] = v[k] = 0.f;
+        if (xo < W && y < H) {
+            u[k] = __ldg(f + y * W + xo);
+            v[k] = __ldg(f + HW + y * W + xo);
+        }
+    }
+    __syncthreads();
+    const int wx0 = org[0], wy0 = org[1];
+    unsigned long long *plane = acc + (size_t)b * HW;
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const int y = ty0 + ly + k * (kBlock / kTW);
+        if (xo < W && y < H) {
+            const Axis ax = splat_axis(xo, u[k], W);
+            const Axis ay = splat_axis(y, v[k], H);
+            const unsigned long long tap[4] = {
+                splat_fix(ax.lo_ok && ay.lo_ok, __fmul_rn(ax.w_lo, ay.w_lo)),
+                splat_fix(ax.hi_ok && ay.lo_ok, __fmul_rn(ax.w_hi, ay.w_lo)),
+                splat_fix(ax.lo_ok && ay.hi_ok, __fmul_rn(ax.w_lo, ay.w_hi)),
+                splat_fix(ax.hi_ok && ay.hi_ok, __fmul_rn(ax.w_hi, ay.w_hi))};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (tap[j]) {  // non-zero implies the target is inside the image
+                    const int X = ax.lo + (j & 1), Y = ay.lo + (j >> 1);
+                    const int rx = X - wx0, ry = Y - wy0;
+                    if ((unsigned)rx < (unsigned)kWW && (unsigned)ry < (unsigned)kWH)
+                        atomicAdd(&win[ry * kWW + rx], tap[j]);
+                    else
+                        atomicAdd(plane + Y * W + X, tap[j]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kWH * kWW; i += kBlock) {
+        const unsigned long long s = win[i];
+        if (s) {
+            const int ry = i / kWW, rx = i - ry * kWW;
+            atomicAdd(plane + (wy0 + ry) * W + (wx0 + rx), s);
+        }
+    }
+}
+
 // occ = clamp(range, 0, 1) < th (warp_utils.py:124-126); the range map itself is written too when asked for.
 __global__ void __launch_bounds__(kBlock)
 occ_threshold_kernel(const unsigned long long *__restrict__ acc, float *__restrict__ occ,
@@ -198,6 +280,18 @@ int occ_backward(const float *flow21, float *occ, float *range_map, int B, int H
         const char *e = getenv("USF_OCC_ITER");
         return (e && e[0] == '4') ? 4 : 1;
     }();
+    static const bool tile = [] {  // opt-in shared-memory window variant
+        const char *e = getenv("USF_OCC_TILE");
+        return e && e[0] == '1';
+    }();
+    if (tile) {
+        const int tiles_x = (W + kTW - 1) / kTW, tiles_y = (H + kTH - 1) / kTH;
+        int st = note_launch(usf_launch(occ_splat_tile_kernel, dim3((unsigned)((size_t)B * tiles_x * tiles_y)), dim3(kBlock), 0,
+                                        stream, flow21, acc, H, W, tiles_x, tiles_y));
+        if (st != USF_OK) return st;
+        return note_launch(usf_launch(occ_threshold_kernel, dim3(blocks), dim3(kBlock), 0, stream,
+                                      (const unsigned long long *)acc, occ, range_map, N, th));
+    }
     const int sblocks = (N + kBlock * iter - 1) / (kBlock * iter);
     cudaError_t le;
 #define USF_SPLAT(M, I) \
