@@ -41,6 +41,27 @@ def test_no_cpu_fallback():
         unsamflow_b200.flow_warp(x, torch.zeros(1, 2, 4, 4))
 
 
+def test_occlusion_masks_match_reference_signatures_and_fail_loudly_on_cpu():
+    # utils/warp_utils.py:109: get_occu_mask_bidirection(flow12, flow21, scale=0.01, bias=0.5)
+    params = list(inspect.signature(unsamflow_b200.get_occu_mask_bidirection).parameters.values())
+    assert [(p.name, p.default) for p in params] == [("flow12", inspect.Parameter.empty), ("flow21", inspect.Parameter.empty),
+                                                     ("scale", 0.01), ("bias", 0.5)]
+    # utils/warp_utils.py:120: get_occu_mask_backward(flow21, th=0.2)
+    params = list(inspect.signature(unsamflow_b200.get_occu_mask_backward).parameters.values())
+    assert [(p.name, p.default) for p in params] == [("flow21", inspect.Parameter.empty), ("th", 0.2)]
+    flow = torch.zeros(1, 2, 4, 4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        unsamflow_b200.get_occu_mask_backward(flow)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        unsamflow_b200.get_occu_mask_bidirection(flow, flow)
+    with pytest.raises(ValueError):
+        unsamflow_b200.get_occu_mask_backward(torch.zeros(1, 3, 4, 4))
+    # the loss takes its visibility masks from the kernel: on a CPU tensor it must raise, not fall back
+    from unsamflow_b200.flow_loss import UnFlowLoss
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        UnFlowLoss()([torch.zeros(1, 4, 8, 8)], torch.zeros(1, 3, 8, 8), torch.zeros(1, 3, 8, 8))
+
+
 def test_product_never_imports_the_oracle():
     import os
     import re

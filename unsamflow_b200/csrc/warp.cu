@@ -38,10 +38,6 @@ constexpr int kSlots = 8;  // list capacity per target pixel
 constexpr int kSlotsS = 16;  // ... in the shared-memory lists of the fused small-image kernel
 
 
-__device__ __forceinline__ float ldp(const float *__restrict__ base, int off, bool ok) {
-    return ok ? __ldg(base + off) : 0.f;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Persistent over pixel blocks (grid = resident CTAs when the level has more blocks than that): the flow of
 // the NEXT block is requested before the taps of the current one are consumed, so a thread's life is one
