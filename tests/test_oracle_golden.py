@@ -130,3 +130,37 @@ def test_oracle_occ_backward_properties():
     flow[0, 1, 4, 4] = np.inf
     _, rng2 = c_oracle.occ_backward(flow)
     assert np.isfinite(rng2).all() and abs(float(rng2.astype(np.float64).sum()) - 142.0) < 1e-4
+
+
+# ---- size-independent properties of the oracle itself (ragged shapes the fixtures do not hold) ---------------------
+@pytest.mark.parametrize("shape", [(1, 1, 1, 1), (2, 3, 2, 17), (1, 33, 11, 5), (3, 4, 9, 9), (1, 196, 3, 10)])
+def test_oracle_corr_adjoint_identities(shape):
+    """The cost volume is bilinear in (x1, x2):  <out, g> = <x1, gx1> = <x2, gx2>."""
+    rs = np.random.RandomState(sum(shape))
+    B, C, H, W = shape
+    x1, x2 = rs.randn(*shape).astype(np.float32), rs.randn(*shape).astype(np.float32)
+    g = rs.randn(B, 81, H, W).astype(np.float32)
+    out = c_oracle.corr_fwd(x1, x2).astype(np.float64)
+    gx1, gx2 = c_oracle.corr_bwd(x1, x2, g)
+    lhs = float((out * g).sum())
+    scale = float(np.abs(out * g).sum()) + 1e-30
+    assert abs(lhs - float((x1.astype(np.float64) * gx1).sum())) <= 1e-5 * scale
+    assert abs(lhs - float((x2.astype(np.float64) * gx2).sum())) <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("pad", ["border", "zeros"])
+@pytest.mark.parametrize("shape", [(1, 1, 2, 2), (2, 3, 5, 17), (1, 7, 13, 4)])
+def test_oracle_warp_is_linear_in_x_with_adjoint_gx(shape, pad):
+    """flow_warp is linear in x for a fixed flow:  <warp(x), g> = <x, gx>, and gx does not depend on x."""
+    rs = np.random.RandomState(sum(shape) + len(pad))
+    B, C, H, W = shape
+    x = rs.randn(*shape).astype(np.float32)
+    flow = (2.5 * rs.randn(B, 2, H, W)).astype(np.float32)
+    g = rs.randn(*shape).astype(np.float32)
+    out = c_oracle.warp_fwd(x, flow, pad).astype(np.float64)
+    gx, _ = c_oracle.warp_bwd(x, flow, g, pad)
+    lhs = float((out * g).sum())
+    scale = float(np.abs(out * g).sum()) + 1e-30
+    assert abs(lhs - float((x.astype(np.float64) * gx).sum())) <= 1e-5 * scale
+    gx_other, _ = c_oracle.warp_bwd(rs.randn(*shape).astype(np.float32), flow, g, pad)
+    assert np.array_equal(gx, gx_other)
