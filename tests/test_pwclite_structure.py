@@ -103,3 +103,39 @@ def test_matches_reference_model_weights_and_outputs(cpu_ops):
     ref_loss = unFlowLoss(loss_cfg)(flows, i1, i2)[0]
     my_loss = flow_loss_mod.UnFlowLoss()(flows, i1, i2)
     assert torch.allclose(ref_loss, my_loss, rtol=1e-4, atol=1e-6), (ref_loss, my_loss)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_every_reference_call_site_binds_to_the_drop_in_signatures():
+    """Parse the reference's sources, find every call of the four functions / one class this repo replaces, and
+    bind its positional and keyword arguments against OUR signatures: a drop-in must accept them all."""
+    import ast
+    import inspect
+
+    import unsamflow_b200 as usf
+    targets = {"flow_warp": inspect.signature(usf.flow_warp),
+               "get_occu_mask_backward": inspect.signature(usf.get_occu_mask_backward),
+               "get_occu_mask_bidirection": inspect.signature(usf.get_occu_mask_bidirection),
+               "Correlation": inspect.signature(usf.Correlation.__init__)}
+    seen = {k: 0 for k in targets}
+    for dirpath, _, files in os.walk(REF):
+        if "correlation_package" in dirpath:
+            continue
+        for fn in files:
+            if not fn.endswith(".py") or fn == "correlation_native.py":
+                continue
+            path = os.path.join(dirpath, fn)
+            try:
+                tree = ast.parse(open(path).read())
+            except SyntaxError:
+                continue
+            for node in ast.walk(tree):
+                if isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id in targets:
+                    name = node.func.id
+                    args = [object()] * (len(node.args) + (1 if name == "Correlation" else 0))  # + self
+                    kwargs = {k.arg: object() for k in node.keywords if k.arg}
+                    targets[name].bind(*args, **kwargs)   # raises TypeError if our signature cannot take the call
+                    seen[name] += 1
+    # models/pwclite.py:208,302,355; losses/flow_loss.py:102-106,130-131; utils/warp_utils.py:110; oc_transforms.py:147-148
+    assert seen["flow_warp"] >= 7 and seen["get_occu_mask_backward"] >= 2, seen
+    assert seen["get_occu_mask_bidirection"] >= 2 and seen["Correlation"] >= 1, seen
