@@ -28,6 +28,7 @@ def cpu_ops(monkeypatch):
     monkeypatch.setattr(pwclite_mod, "flow_warp", torch_port.flow_warp)
     monkeypatch.setattr(flow_loss_mod, "flow_warp", torch_port.flow_warp)
     monkeypatch.setattr(flow_loss_mod, "get_occu_mask_backward", torch_port.occ_mask_backward)
+    monkeypatch.setattr(flow_loss_mod, "get_occu_mask_bidirection", torch_port.occ_mask_bidirection)
 
 
 def test_parameter_count_and_output_shapes(cpu_ops):
@@ -102,6 +103,11 @@ def test_matches_reference_model_weights_and_outputs(cpu_ops):
                    with_bk=True)
     ref_loss = unFlowLoss(loss_cfg)(flows, i1, i2)[0]
     my_loss = flow_loss_mod.UnFlowLoss()(flows, i1, i2)
+    assert torch.allclose(ref_loss, my_loss, rtol=1e-4, atol=1e-6), (ref_loss, my_loss)
+    # the other visibility mask of the reference (occ_from_back = false: forward-backward consistency)
+    loss_cfg.occ_from_back = False
+    ref_loss = unFlowLoss(loss_cfg)(flows, i1, i2)[0]
+    my_loss = flow_loss_mod.UnFlowLoss(occ_from_back=False)(flows, i1, i2)
     assert torch.allclose(ref_loss, my_loss, rtol=1e-4, atol=1e-6), (ref_loss, my_loss)
 
 

@@ -20,7 +20,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .occlusion import get_occu_mask_backward
+from .occlusion import get_occu_mask_backward, get_occu_mask_bidirection
 from .warp import flow_warp
 
 
@@ -37,9 +37,11 @@ def ssim_distance(x, y):
 
 
 class UnFlowLoss(nn.Module):
-    def __init__(self, w_l1=0.15, w_ssim=0.85, w_scales=(1.0, 1.0, 1.0, 1.0, 0.0), warp_pad="border"):
+    def __init__(self, w_l1=0.15, w_ssim=0.85, w_scales=(1.0, 1.0, 1.0, 1.0, 0.0), warp_pad="border",
+                 occ_from_back=True):
         super().__init__()
         self.w_l1, self.w_ssim, self.w_scales, self.warp_pad = w_l1, w_ssim, w_scales, warp_pad
+        self.occ_from_back = occ_from_back
 
     def photometric(self, target, recons, vis):
         terms = []
@@ -54,8 +56,12 @@ class UnFlowLoss(nn.Module):
         (trainer/kitti_trainer_ar.py:115-127)."""
         top = pyramid_flows[0]
         # occ_from_back (losses/flow_loss.py:99-106): range-map masks of the finest flows, no gradient
-        vis1 = 1 - get_occu_mask_backward(top[:, 2:].detach())
-        vis2 = 1 - get_occu_mask_backward(top[:, :2].detach())
+        if self.occ_from_back:
+            vis1 = 1 - get_occu_mask_backward(top[:, 2:].detach(), th=0.2)
+            vis2 = 1 - get_occu_mask_backward(top[:, :2].detach(), th=0.2)
+        else:  # forward-backward consistency (losses/flow_loss.py:104-106)
+            vis1 = 1 - get_occu_mask_bidirection(top[:, :2].detach(), top[:, 2:].detach())
+            vis2 = 1 - get_occu_mask_bidirection(top[:, 2:].detach(), top[:, :2].detach())
         total = 0.0
         for i, flow in enumerate(pyramid_flows):
             if self.w_scales[i] <= 0:
