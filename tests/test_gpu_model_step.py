@@ -179,3 +179,56 @@ def test_training_step_gradients_within_the_networks_own_noise_floor(exact_math,
     assert g_usf.keys() == g_ref.keys() and len(g_ref) > 50
     assert floor < 5e-2, floor
     assert ours <= 3.0 * floor + 1e-6, (ours, floor)
+
+
+def _mf_step_main():
+    """Body of test_mask_feature_config_step_on_the_usf_ops; runs in its own process (see there)."""
+    import unsamflow_b200 as usf
+    import unsamflow_b200.pwclite as pw
+    from functools import partial
+    from oracle import torch_port
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+
+    def flows_with(corr_cls, warp):
+        pw.Correlation, pw.flow_warp = corr_cls, warp
+        torch.manual_seed(8)
+        model = pw.PWCLite(add_mask_corr=True, aggregation_type="concat").cuda()
+        model.init_weights()
+        gen = torch.Generator().manual_seed(9)
+        img1, img2 = torch.rand(*SHAPE, generator=gen).cuda(), torch.rand(*SHAPE, generator=gen).cuda()
+        coarse = torch.randint(0, 40, (SHAPE[0], 1, 8, 28), generator=gen).float()
+        seg1 = torch.nn.functional.interpolate(coarse, SHAPE[-2:], mode="nearest").cuda()
+        seg2 = torch.roll(seg1, 9, dims=-1)
+        out = model(img1, img2, seg1, seg2, with_bk=True)
+        loss = sum(f.abs().mean() for f in out["flows_12"] + out["flows_21"])
+        loss.backward()
+        assert all(torch.isfinite(p.grad).all() for p in model.parameters())
+        return [f.detach() for f in out["flows_12"] + out["flows_21"]]
+
+    port = flows_with(PortCorrelation, torch_port.flow_warp)
+    mine = flows_with(usf.Correlation, partial(usf.flow_warp, coord_reciprocal=True))
+    worst = max(rel(a, b) for a, b in zip(mine, port))
+    assert worst <= 1e-3, worst
+    print("mf step ok, worst flow rel-L2", worst)
+
+
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: not yet run on a B200 "
+                                        "(the +mf caller is checked against the reference on CPU in "
+                                        "tests/test_pwclite_structure.py)")
+def test_mask_feature_config_step_on_the_usf_ops():
+    """BASELINE.json configs[3] (kitti_aug+hg+mf): the restated caller with add_mask_corr=True runs its second
+    flow_warp / Correlation pair (models/pwclite.py:355-356; C=32 at every level, zero flow at the coarsest) on the
+    usf kernels and agrees with the same model on the ported ops.  Runs in a subprocess: the test has not been
+    on a GPU yet and must not be able to disturb the CUDA context of the tests that follow."""
+    import os
+    import subprocess
+    import sys
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_model_step as t; "
+            "t._mf_step_main()" % (os.path.dirname(here), here))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]

@@ -145,3 +145,77 @@ def test_every_reference_call_site_binds_to_the_drop_in_signatures():
     # models/pwclite.py:208,302,355; losses/flow_loss.py:102-106,130-131; utils/warp_utils.py:110; oc_transforms.py:147-148
     assert seen["flow_warp"] >= 7 and seen["get_occu_mask_backward"] >= 2, seen
     assert seen["get_occu_mask_bidirection"] >= 2 and seen["Correlation"] >= 1, seen
+
+
+def _onehot_pool(feat, seg):
+    """The reference's formulation, models/pwclite.py:319-328."""
+    oh = torch.nn.functional.one_hot(seg.long())
+    pooled = torch.amax(oh * feat[..., None], dim=(2, 3))
+    return (oh * pooled[:, :, None, None, :]).sum(dim=-1)
+
+
+@pytest.mark.parametrize("case", ["random_ids", "one_segment_covers_all", "negative_features", "gaps_in_ids"])
+def test_segment_max_pool_equals_the_one_hot_formulation(case):
+    gen = torch.Generator().manual_seed(3)
+    feat = torch.randn(2, 5, 6, 7, generator=gen)
+    seg = torch.randint(0, 9, (2, 1, 6, 7), generator=gen).float()
+    if case == "one_segment_covers_all":
+        seg = torch.zeros(2, 1, 6, 7)
+    if case == "negative_features":
+        feat = -feat.abs() - 0.1          # every segment maximum is negative -> the reference pools to 0
+    if case == "gaps_in_ids":
+        seg = seg * 3                     # ids 0,3,6,...: empty classes in between
+    a = feat.clone().requires_grad_(True)
+    b = feat.clone().requires_grad_(True)
+    mine, ref = pwclite_mod.segment_max_pool(a, seg), _onehot_pool(b, seg)
+    assert torch.equal(mine, ref)
+    g = torch.randn(mine.shape, generator=gen)
+    mine.backward(g)
+    ref.backward(g)
+    assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-5)   # the sums over a segment run in another order
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+@pytest.mark.parametrize("aggregation", ["concat", "residual"])
+def test_mask_feature_branch_matches_reference(cpu_ops, aggregation):
+    """`+mf` configs (configs/kitti_aug+hg+mf.json:3-6: add_mask_corr, aggregation_type): the restated caller with
+    the extra flow_warp / Correlation pair (models/pwclite.py:355-356) against the reference model, same weights,
+    SAM-shaped synthetic segment ids (piecewise-constant, <= 40 ids; SURVEY.md 8d config #4)."""
+    sys.path.insert(0, REF)
+    sys.modules.setdefault("correlation_cuda", types.ModuleType("correlation_cuda"))
+    try:
+        import models.pwclite as ref_pwc
+        from models.correlation_native import Correlation as RefCorr
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"reference not importable here: {e!r}")
+
+    class Cfg(dict):
+        __getattr__ = dict.__getitem__
+        __setattr__ = dict.__setitem__
+
+    ref_pwc.Correlation = RefCorr
+    torch.manual_seed(4)
+    ref = ref_pwc.PWCLite(Cfg(reduce_dense=True, learned_upsampler=True, add_mask_corr=True,
+                              aggregation_type=aggregation))
+    ref.init_weights()
+    mine = pwclite_mod.PWCLite(add_mask_corr=True, aggregation_type=aggregation)
+    if aggregation == "concat":
+        assert mine.num_parameters() == ref.num_parameters() == 2625348   # SURVEY.md 8c
+    rs, ms = ref.state_dict(), mine.state_dict()
+    assert [tuple(v.shape) for v in rs.values()] == [tuple(v.shape) for v in ms.values()]
+    mine.load_state_dict({k: v for k, v in zip(ms.keys(), rs.values())})
+    i1, i2 = torch.rand(2, 3, 64, 128), torch.rand(2, 3, 64, 128)
+    coarse = torch.randint(0, 40, (2, 1, 4, 8)).float()
+    s1 = torch.nn.functional.interpolate(coarse, (64, 128), mode="nearest")
+    s2 = torch.roll(s1, 5, dims=-1)
+    with torch.no_grad():
+        o_ref, o_mine = ref(i1, i2, s1, s2, with_bk=True), mine(i1, i2, s1, s2, with_bk=True)
+        both = pwclite_mod.PWCLite(batch_directions=True, add_mask_corr=True, aggregation_type=aggregation)
+        both.load_state_dict(mine.state_dict())
+        o_both = both(i1, i2, s1, s2, with_bk=True)
+    for k in ("flows_12", "flows_21"):
+        for a, b, c in zip(o_ref[k], o_mine[k], o_both[k]):
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), k
+            assert torch.allclose(a, c, rtol=1e-4, atol=1e-4), k
+    with pytest.raises(ValueError):
+        mine(i1, i2, with_bk=True)

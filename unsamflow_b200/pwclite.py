@@ -2,12 +2,19 @@
 
 Scope note: the product of this repo is the correlation + warp path; this
 module restates the network around it (models/pwclite.py:14-434, base configuration:
-reduce_dense=True, learned_upsampler=True, no mask-correlation branch) only so that the path can
-be exercised and timed inside a real training step without the reference tree on the box.  All
-learned layers are plain PyTorch / cuDNN, exactly as in the reference; the two call sites are
+reduce_dense=True, learned_upsampler=True; optionally the mask-feature branch of the `+mf` configs,
+add_mask_corr=True, configs/kitti_aug+hg+mf.json:3-6) only so that the path can be exercised and timed inside a
+real training step without the reference tree on the box.  All learned layers are plain PyTorch / cuDNN,
+exactly as in the reference; the call sites are
 
-    x2_warp = flow_warp(x2, flow)          models/pwclite.py:302
-    out_corr = self.corr(x1, x2_warp)      models/pwclite.py:307
+    x2_warp = flow_warp(x2, flow)                                 models/pwclite.py:302
+    out_corr = self.corr(x1, x2_warp)                             models/pwclite.py:307
+    x_mask_feat2_warp = flow_warp(x_mask_feat2, flow)             models/pwclite.py:355   (add_mask_corr)
+    out_mask_corr = self.corr(x_mask_feat1, x_mask_feat2_warp)    models/pwclite.py:356   (add_mask_corr)
+
+The segment pooling in front of the second pair (models/pwclite.py:317-340) is restated as a segmented max +
+gather (`segment_max_pool`) instead of the reference's one-hot product, whose [B,32,h,w,N] temporaries reach
+gigabytes at B=8; same values and gradients.
 
 Layer shapes follow the reference so that the parameter count (2,513,412) and a state-dict loaded
 position-by-position from the reference model agree (tests/test_pwclite_structure.py).
@@ -103,19 +110,52 @@ class ConvexUpsampler(nn.Module):
         return up.reshape(n, 2, s * h, s * w)
 
 
+def segment_max_pool(feat, seg):
+    """feat [B,C,h,w], seg [B,1,h,w] integer ids -> every pixel receives the maximum of `feat` over its segment.
+
+    Restates models/pwclite.py:319-328: `amax(one_hot(seg) * feat[..., None], dim=(2, 3))` followed by the
+    one-hot weighted sum.  In that product the pixels outside a segment contribute zeros, so the pooled value is
+    max(0, max over the segment) unless the segment covers the whole image -- reproduced here by reducing into a
+    zero-initialised table (and into -inf for an all-covering segment)."""
+    b, c, h, w = feat.shape
+    ids = seg.reshape(b, 1, h * w).long()
+    n = int(ids.max().item()) + 1
+    idx = ids.expand(b, c, h * w)
+    table = feat.new_zeros(b, c, n)
+    covers_all = feat.new_zeros(b, 1, n).scatter_add_(2, ids, feat.new_ones(b, 1, h * w)) == h * w
+    table = table.masked_fill(covers_all, float("-inf"))
+    table = table.scatter_reduce(2, idx, feat.reshape(b, c, h * w), "amax", include_self=True)
+    return table.gather(2, idx).reshape(b, c, h, w)
+
+
 class PWCLite(nn.Module):
-    def __init__(self, batch_directions=False):
+    def __init__(self, batch_directions=False, add_mask_corr=False, aggregation_type="concat"):
         super().__init__()
         self.batch_directions = batch_directions
+        self.add_mask_corr = add_mask_corr
+        self.aggregation_type = aggregation_type
+        if aggregation_type not in ("concat", "residual"):
+            raise NotImplementedError(f"aggregation_type={aggregation_type!r}")  # models/pwclite.py:350-351
         self.feature_pyramid_extractor = FeaturePyramid()
         self.corr = Correlation(pad_size=SEARCH_RANGE, kernel_size=1, max_displacement=SEARCH_RANGE, stride1=1,
                                 stride2=1, corr_multiply=1)
         self.leaky = nn.LeakyReLU(0.1, inplace=True)
         dim_corr = (2 * SEARCH_RANGE + 1) ** 2
-        self.flow_estimators = FlowEstimator(32 + dim_corr + 2)
+        self.flow_estimators = FlowEstimator(32 + (2 if add_mask_corr else 1) * dim_corr + 2)
         self.context_networks = ContextNetwork(self.flow_estimators.feat_dim + 2)
         self.output_flow_upsampler = ConvexUpsampler(96, 4)
         self.conv_1x1 = nn.ModuleList(conv_block(c, 32, kernel_size=1) for c in PYRAMID_CHANNELS[:1:-1])
+        if add_mask_corr:  # models/pwclite.py:249-269 (registered after conv_1x1, like the reference)
+            self.conv_1x1_mask = nn.ModuleList(conv_block(c, 32, kernel_size=1) for c in PYRAMID_CHANNELS[:1:-1])
+            self.mask_aggregation = conv_block(64 if aggregation_type == "concat" else 32, 32, kernel_size=1)
+
+    def mask_features(self, level, x, seg):
+        """models/pwclite.py:317-351 for one image: 1x1 conv, pooling over the SAM segments, aggregation."""
+        proj = self.conv_1x1_mask[level](x)
+        pooled = segment_max_pool(proj, F.interpolate(seg, x.shape[-2:], mode="nearest"))
+        if self.aggregation_type == "residual":
+            return proj + self.mask_aggregation(pooled)
+        return self.mask_aggregation(torch.cat([proj, pooled], 1))
 
     def init_weights(self):
         for m in self.modules():
@@ -126,7 +166,7 @@ class PWCLite(nn.Module):
     def num_parameters(self):
         return sum(p.numel() for p in self.parameters() if p.requires_grad)
 
-    def decoder(self, pyr1, pyr2):
+    def decoder(self, pyr1, pyr2, seg1=None, seg2=None):
         flows = []
         b, _, h0, w0 = pyr1[0].shape
         flow = torch.zeros(b, 2, h0, w0, dtype=torch.float32, device=pyr1[0].device)
@@ -137,7 +177,14 @@ class PWCLite(nn.Module):
             else:
                 x2_warp = x2
             cost = self.leaky(self.corr(x1, x2_warp))
-            feat, flow_res = self.flow_estimators(torch.cat([cost, self.conv_1x1[level](x1), flow], 1))
+            x1_proj = self.conv_1x1[level](x1)
+            if self.add_mask_corr:
+                m1, m2 = self.mask_features(level, x1, seg1), self.mask_features(level, x2, seg2)
+                # the reference warps with `flow` at every level, the all-zero initial flow included (:355)
+                mask_cost = self.leaky(self.corr(m1, flow_warp(m2, flow)))
+                feat, flow_res = self.flow_estimators(torch.cat([cost, mask_cost, x1_proj, flow], 1))
+            else:
+                feat, flow_res = self.flow_estimators(torch.cat([cost, x1_proj, flow], 1))
             flow = flow + flow_res
             flow_fine, up_feat = self.context_networks(torch.cat([feat, flow], 1))
             flow = flow + flow_fine
@@ -147,16 +194,22 @@ class PWCLite(nn.Module):
         return flows[::-1]
 
     def forward(self, img1, img2, full_seg1=None, full_seg2=None, with_bk=False):
-        if full_seg1 is not None or full_seg2 is not None:
-            raise NotImplementedError("segmentation inputs (add_mask_corr / input_adj_map) are not restated here")
+        if self.add_mask_corr and (full_seg1 is None or full_seg2 is None):
+            raise ValueError("add_mask_corr=True needs full_seg1 / full_seg2 ([B,1,H,W] segment ids)")
+        if not self.add_mask_corr and (full_seg1 is not None or full_seg2 is not None):
+            raise NotImplementedError("segmentation inputs without add_mask_corr (input_adj_map / input_boundary) "
+                                      "are not restated here")
         feat1 = self.feature_pyramid_extractor(img1)
         feat2 = self.feature_pyramid_extractor(img2)
         if with_bk and self.batch_directions:
             n = img1.shape[0]
+            seg12 = seg21 = None
+            if self.add_mask_corr:
+                seg12, seg21 = torch.cat([full_seg1, full_seg2]), torch.cat([full_seg2, full_seg1])
             both = self.decoder([torch.cat([a, b]) for a, b in zip(feat1, feat2)],
-                                [torch.cat([b, a]) for a, b in zip(feat1, feat2)])
+                                [torch.cat([b, a]) for a, b in zip(feat1, feat2)], seg12, seg21)
             return {"flows_12": [f[:n] for f in both], "flows_21": [f[n:] for f in both]}
-        out = {"flows_12": self.decoder(feat1, feat2)}
+        out = {"flows_12": self.decoder(feat1, feat2, full_seg1, full_seg2)}
         if with_bk:
-            out["flows_21"] = self.decoder(feat2, feat1)
+            out["flows_21"] = self.decoder(feat2, feat1, full_seg2, full_seg1)
         return out
