@@ -420,10 +420,8 @@ def run_ours(args):
         del gA, gB, gFull
         train_ms, train_info = time_train_step(args, local, world, barrier)
 
-    stats = torch.tensor([total_ms, e2e_ms, train_ms], dtype=torch.float64, device=step.device)
-    if dist is not None:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, train_ms = stats.tolist()
+    from unsamflow_b200 import dist_util
+    total_ms, e2e_ms, train_ms = dist_util.max_over_ranks([total_ms, e2e_ms, train_ms])  # NCCL: on this rank's GPU
 
     if rank == 0:
         peak, peak_src = peaks()

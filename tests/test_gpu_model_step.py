@@ -214,14 +214,11 @@ def _mf_step_main():
     print("mf step ok, worst flow rel-L2", worst)
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: not yet run on a B200 "
-                                        "(the +mf caller is checked against the reference on CPU in "
-                                        "tests/test_pwclite_structure.py)")
 def test_mask_feature_config_step_on_the_usf_ops():
     """BASELINE.json configs[3] (kitti_aug+hg+mf): the restated caller with add_mask_corr=True runs its second
     flow_warp / Correlation pair (models/pwclite.py:355-356; C=32 at every level, zero flow at the coarsest) on the
-    usf kernels and agrees with the same model on the ported ops.  Runs in a subprocess: the test has not been
-    on a GPU yet and must not be able to disturb the CUDA context of the tests that follow."""
+    usf kernels and agrees with the same model on the ported ops.  Runs in a subprocess so that it cannot
+    disturb the CUDA context of the tests that follow (passed on a B200 at the end of round 1)."""
     import os
     import subprocess
     import sys

@@ -393,6 +393,33 @@ def test_errors_are_loud(usf):
         ops.corr_fwd(x.half(), x.half())          # fp16 is not a supported storage type
     with pytest.raises(ValueError):
         ops.corr_fwd(x, x.bfloat16())
+    # caller-supplied buffers reach the kernels as raw pointers: wrong shape / dtype / layout / device must raise
+    fl, go = torch.zeros(1, 2, 8, 8).cuda(), torch.zeros(1, 81, 8, 8).cuda()
+    with pytest.raises(ValueError, match="out=: shape"):
+        ops.corr_fwd(x, x, out=torch.empty(1, 81, 8, 7).cuda())
+    with pytest.raises(ValueError, match="out=: dtype"):
+        ops.corr_fwd(x.bfloat16(), x.bfloat16(), out=torch.empty(1, 81, 8, 8).cuda())
+    with pytest.raises(ValueError, match="contiguous"):
+        ops.corr_fwd(x, x, out=torch.empty(1, 81, 8, 16).cuda()[..., ::2])
+    with pytest.raises(ValueError, match="out=: device"):
+        ops.corr_fwd(x, x, out=torch.empty(1, 81, 8, 8))
+    with pytest.raises(ValueError, match="gx1=: shape"):
+        ops.corr_bwd(x, x, go, gx1=torch.empty(1, 4, 8, 4).cuda())
+    with pytest.raises(ValueError, match="gx2=: dtype"):
+        ops.corr_bwd(x, x, go, gx2=torch.empty(1, 4, 8, 8, dtype=torch.bfloat16).cuda())
+    with pytest.raises(ValueError, match="out=: shape"):
+        ops.warp_fwd(x, fl, out=torch.empty(1, 4, 8, 9).cuda())
+    with pytest.raises(ValueError, match="gx=: contiguous|gx=: must be contiguous"):
+        ops.warp_bwd(x, fl, x, gx=torch.empty(1, 4, 8, 16).cuda()[..., ::2])
+    with pytest.raises(ValueError, match="gflow=: dtype"):
+        ops.warp_bwd(x, fl, x, gflow=torch.empty(1, 2, 8, 8, dtype=torch.bfloat16).cuda())
+    big = torch.zeros(1, 4, 40, 40).cuda()
+    with pytest.raises(ValueError, match="workspace"):
+        ops.warp_bwd(big, torch.zeros(1, 2, 40, 40).cuda(), big, workspace=torch.empty(16, dtype=torch.uint8).cuda())
+    with pytest.raises(ValueError, match="out=: shape"):
+        ops.occ_bidirection(fl, fl, out=torch.empty(1, 2, 8, 8).cuda())
+    with pytest.raises(ValueError, match="out=: dtype"):
+        ops.occ_backward(fl, out=torch.empty(1, 1, 8, 8, dtype=torch.float64).cuda())
 
 
 def test_cuda_graph_capture_of_a_step(usf):

@@ -62,6 +62,27 @@ def test_occlusion_masks_match_reference_signatures_and_fail_loudly_on_cpu():
         UnFlowLoss()([torch.zeros(1, 4, 8, 8)], torch.zeros(1, 3, 8, 8), torch.zeros(1, 3, 8, 8))
 
 
+def test_preallocated_buffers_are_validated():
+    """ops._check_out / _check_ws guard every caller-supplied buffer (they reach the kernels as raw pointers)."""
+    from unsamflow_b200 import ops
+    dev = torch.device("cpu")
+    good = torch.empty(2, 3, 4, 5)
+    assert ops._check_out(good, (2, 3, 4, 5), torch.float32, dev, "out") is good
+    assert ops._check_out(None, (1,), torch.float32, dev, "out") is None
+    for bad, pat in ((torch.empty(2, 3, 4, 6), "shape"), (torch.empty(2, 3, 4, 5, dtype=torch.bfloat16), "dtype"),
+                     (torch.empty(2, 3, 4, 10)[..., ::2], "contiguous"), ("not a tensor", "expected a tensor")):
+        with pytest.raises(ValueError, match=pat):
+            ops._check_out(bad, (2, 3, 4, 5), torch.float32, dev, "out")
+    with pytest.raises(ValueError, match="device"):
+        ops._check_out(good, (2, 3, 4, 5), torch.float32, torch.device("cuda", 0), "out")
+    ws = torch.empty(64, dtype=torch.uint8)
+    assert ops._check_ws(ws, 64, dev) is ws
+    with pytest.raises(ValueError, match="need 65"):
+        ops._check_ws(ws, 65, dev)
+    with pytest.raises(ValueError, match="aligned"):
+        ops._check_ws(torch.empty(128, dtype=torch.uint8)[1:], 64, dev)
+
+
 def test_product_never_imports_the_oracle():
     import os
     import re

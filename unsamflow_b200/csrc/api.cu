@@ -40,6 +40,20 @@ long kDirectMaxPixels = [] {
     return e ? atol(e) : 4096L;
 }();
 
+int sm_count() {
+    static std::mutex mu;
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache[dev] == 0) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+        cache[dev] = sms;
+    }
+    return cache[dev];
+}
+
 bool pdl_enabled() {
     static const bool on = [] {
         const char *e = getenv("USF_PDL");

@@ -31,6 +31,8 @@ cudaError_t ensure_smem(const void *kernel, int smem_bytes);
 // longer waits for the predecessor to drain, which is a microsecond or two per dependent kernel in a chain of
 // ~30.  USF_PDL=0 launches without the attribute (the wait is then a no-op).
 bool pdl_enabled();  // api.cu
+// SMs of the current device (cudaDevAttrMultiProcessorCount, cached per device; 148 on B200): grid sizing
+int sm_count();      // api.cu
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 template <typename... KArgs, typename... Args>
 inline cudaError_t usf_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

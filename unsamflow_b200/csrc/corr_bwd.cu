@@ -544,7 +544,7 @@ inline bool thin_grid(int B, int C, int H, int W, int ngrad) {
     static const int force = [] { const char *e = getenv("USF_BWD_THIN"); return e ? atoi(e) : -1; }();
     if (force >= 0) return force != 0;
     const long ctas = (long)((W + TW - 1) / TW) * ((H + TH - 1) / TH) * B * ((C + CG - 1) / CG) * ngrad;
-    return ctas * 4 < 148L * 2 * 3;
+    return ctas * 4 < (long)sm_count() * 2 * 3;
 }
 
 template <bool GX2, bool VEC>
@@ -580,7 +580,7 @@ int corr_bwd_f32(const float *x1, const float *x2, const float *gout, float *gx1
             const int ngroups = (C + CG - 1) / CG, nz = B * ngroups;
             const int t32x = (W + TW - 1) / TW, t32y = (H + TH - 1) / TH;
             const int t16x = (W + SQ - 1) / SQ, t16y = (H + SQ - 1) / SQ;
-            const long slots = 148L * 2, now = 2L * t32x * t32y * nz, mix = (long)(t32x * t32y + t16x * t16y) * nz;
+            const long slots = (long)sm_count() * 2, now = 2L * t32x * t32y * nz, mix = (long)(t32x * t32y + t16x * t16y) * nz;
             if ((mix + slots - 1) / slots < (now + slots - 1) / slots &&
                 make_nchw_map(&mx1, x2, B, C, H, W, XS2, XR2, CT) && make_nchw_map(&mg1, gout, B, kK, H, W, GS2, SQ, kD) &&
                 make_nchw_map(&mx2, x1, B, C, H, W, XS, XR, CT) && make_nchw_map(&mg2, gout, B, kK, H, W, XS, TH, kD)) {

@@ -496,16 +496,17 @@ cudaError_t launch_tma(bool splitc, const CUtensorMap &m1, const CUtensorMap &m2
         usf_launch(corr_fwd_splitc_tma<LEAKY>, dim3(dim3(tx, ty, B * kD)), dim3(TB_THREADS), TB_SMEM, stream, m1, m2b, out, C, H, W, rc, slope);
     } else {
         const int ntiles = tx * ty * B;
-        if (ntiles * 2 <= 3 * 148) {  // at most 1.5 tiles per SM: one pipelined CTA per SM
+        const int sms = sm_count();
+        if (ntiles * 2 <= 3 * sms) {  // at most 1.5 tiles per SM: one pipelined CTA per SM
             cudaError_t once = ensure_smem((const void *)corr_fwd_tile9_tma<LEAKY, true>, T9Cfg<true>::kSmem);
             if (once != cudaSuccess) return once;
-            const int grid = ntiles < 148 ? ntiles : 148;
+            const int grid = ntiles < sms ? ntiles : sms;
             usf_launch((corr_fwd_tile9_tma<LEAKY, true>), dim3(grid), dim3(TA_THREADS), T9Cfg<true>::kSmem, stream, 
                 m1, m2a, out, C, H, W, tx, ty, ntiles, rc, slope);
         } else {
             cudaError_t once = ensure_smem((const void *)corr_fwd_tile9_tma<LEAKY, false>, T9Cfg<false>::kSmem);
             if (once != cudaSuccess) return once;
-            const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;
+            const int grid = ntiles < 2 * sms ? ntiles : 2 * sms;
             usf_launch((corr_fwd_tile9_tma<LEAKY, false>), dim3(grid), dim3(TA_THREADS), T9Cfg<false>::kSmem, stream, 
                 m1, m2a, out, C, H, W, tx, ty, ntiles, rc, slope);
         }
@@ -530,7 +531,7 @@ int corr_fwd_f32(const float *x1, const float *x2, float *out, int B, int C, int
     // Few tiles and many channels: split dy over CTAs and channels over warps.
     const long tiles = (long)tx * ty * B;
     // fewer tiles than half the SMs: split dy over CTAs and channels over warps; else persistent tiles
-    const bool splitc = tiles * 2 < 148 && C >= 48;
+    const bool splitc = tiles * 2 < sm_count() && C >= 48;
     if (vec) {
         // TMA path: tensor maps are encoded on the host per call (pointers differ per call) and travel
         // as __grid_constant__ kernel parameters; nothing is cached between calls (re-entrant).

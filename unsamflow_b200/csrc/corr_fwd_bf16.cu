@@ -147,7 +147,7 @@ int corr_fwd_bf16_tiled(const void *x1, const void *x2, void *out, int B, int C,
     if (!make_nchw_map_bf16(&m1, x1, B, C, H, W, X1E, TH, CK) || !make_nchw_map_bf16(&m2, x2, B, C, H, W, X2E, X2R, CK))
         return USF_ERR_UNSUPPORTED;
     const int tx = (W + TW - 1) / TW, ty = (H + TH - 1) / TH, ntiles = tx * ty * B;
-    const int grid = ntiles < 2 * 148 ? ntiles : 2 * 148;
+    const int grid = ntiles < 2 * sm_count() ? ntiles : 2 * sm_count();
     const float rc = 1.0f / (float)C;
     cudaError_t e;
     if (flags & USF_FLAG_LEAKY_RELU) {

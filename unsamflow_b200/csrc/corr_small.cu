@@ -453,7 +453,7 @@ cudaError_t launch_bwd(const T *x1, const T *x2, const T *gout, T *gx1, T *gx2, 
     // 16 channels per CTA halve the copies of gO; 8 per CTA when that is what it takes to cover the SMs
     int NGC = kMaxThreads / P;
     NGC = NGC > 2 ? 2 : (NGC < 1 ? 1 : NGC);
-    if (C <= kCT || (long)B * ngrad * ((C + 2 * kCT - 1) / (2 * kCT)) < 148) NGC = 1;
+    if (C <= kCT || (long)B * ngrad * ((C + 2 * kCT - 1) / (2 * kCT)) < sm_count()) NGC = 1;
     const int CS = NGC * kCT;
     const size_t smem = (((size_t)kK + CS) * HW + 2 * kPad) * 4;
     cudaError_t e = ensure_smem((const void *)corr_bwd_small<PX, T>, (int)smem);

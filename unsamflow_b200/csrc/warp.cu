@@ -549,7 +549,7 @@ int pick_ns(int C, int N) {
     // at least two slices once there are 16 channels: one thread walking 32 channels of a level that does not
     // fit in L2 (64x32x64x208) ran the gather at 10 % of DRAM bandwidth (ncu), two slices at twice that
     int ns = C >= 16 ? 2 : 1;
-    const long wave = 148L * 2048;
+    const long wave = (long)sm_count() * 2048;
     while (ns < 32 && C >= 8 * ns && (ns < 8 ? (long)N * ns < wave : (long)N * ns * 2 <= wave)) ns *= 2;
     return ns;
 }
@@ -566,15 +566,14 @@ static int resident_ctas(const void *kernel) {
     static std::mutex mu;
     static std::map<std::pair<const void *, int>, int> cache;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148 * 4;
+    if (cudaGetDevice(&dev) != cudaSuccess) return sm_count() * 4;
     std::lock_guard<std::mutex> lock(mu);
     auto key = std::make_pair(kernel, dev);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
-    int per_sm = 0, sms = 0;
+    int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kBlock, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
-    return cache[key] = per_sm * sms;
+    return cache[key] = per_sm * sm_count();
 }
 
 template <typename T>
@@ -691,7 +690,7 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
     // fixed grid (the entry count lives on the device), sized for the worst case of this shape: up to 2 CTAs
     // per SM (the list is normally empty or short), grid-stride over entries x channels
     long ovf_blocks = ((long)4 * N * C + 16L * kBlock - 1) / (16L * kBlock);
-    ovf_blocks = ovf_blocks < 16 ? 16 : (ovf_blocks > 148 * 2 ? 148 * 2 : ovf_blocks);
+    ovf_blocks = ovf_blocks < 16 ? 16 : (ovf_blocks > sm_count() * 2 ? sm_count() * 2 : ovf_blocks);
     usf_launch(warp_gx_overflow<T>, dim3((int)ovf_blocks), dim3(kBlock), 0, stream, gout, gx, ws, 4 * N, C, HW);
     return note_launch(cudaGetLastError());
 }

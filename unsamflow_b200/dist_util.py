@@ -33,15 +33,24 @@ def init_from_env(backend=None):
     return dist.get_rank(), dist.get_world_size()
 
 
-def max_over_ranks(values, device="cpu"):
+def _reduce_device(device=None):
+    """NCCL reduces CUDA tensors only: default to this rank's current GPU there, to the CPU under gloo."""
+    if device is not None:
+        return torch.device(device)
+    if dist.is_available() and dist.is_initialized() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def max_over_ranks(values, device=None):
     """Element-wise MAX of a list of floats over all ranks (timings are reported as the slowest rank)."""
-    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    t = torch.tensor(list(values), dtype=torch.float64, device=_reduce_device(device))
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return t.tolist()
 
 
-def aggregate_throughput(units_per_rank, seconds_this_rank, device="cpu"):
+def aggregate_throughput(units_per_rank, seconds_this_rank, device=None):
     """Whole-job throughput: units all ranks processed / slowest rank's time."""
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     (tmax,) = max_over_ranks([seconds_this_rank], device)

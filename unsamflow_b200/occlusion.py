@@ -25,8 +25,11 @@ def get_occu_mask_backward(flow21, th=0.2):
 
 
 @torch.no_grad()
-def get_corresponding_map(flow21):
-    """Range map of `mesh_grid + flow21` (what the reference's get_occu_mask_backward passes to
-    get_corresponding_map, utils/warp_utils.py:122-124).  Takes the FLOW, not the coordinates: the pixel
-    grid is built inside the kernel."""
+def range_map_from_flow(flow21):
+    """Range map of `mesh_grid + flow21`: how many source pixels (bilinearly split) land on each target.
+    This is what the reference's get_occu_mask_backward hands to get_corresponding_map
+    (utils/warp_utils.py:122-124), but the argument here is the FLOW -- the pixel grid is added inside
+    the kernel -- which is why it does not carry the reference's name (a caller ported from the reference
+    would otherwise add the grid twice).  Recovering the flow from absolute coordinates by subtraction is
+    not exact in fp32, so no coordinate-taking variant is offered."""
     return ops.occ_backward(flow21, 0.2, want_range_map=True)[1].to(flow21.dtype)

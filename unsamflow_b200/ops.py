@@ -41,6 +41,34 @@ def _same(a, b, na, nb):
         raise RuntimeError(f"{na} and {nb} are on different devices")
 
 
+def _check_out(t, shape, dtype, device, name):
+    """A caller-supplied buffer goes to the kernels as a raw pointer: it must be exactly what the kernel
+    writes (shape, dtype, device, contiguous) or the device would silently write out of bounds."""
+    if t is None:
+        return None
+    if not isinstance(t, torch.Tensor):
+        raise ValueError(f"{name}=: expected a tensor, got {type(t).__name__}")
+    if tuple(t.shape) != tuple(shape):
+        raise ValueError(f"{name}=: shape {tuple(t.shape)} != {tuple(shape)}")
+    if t.dtype != dtype:
+        raise ValueError(f"{name}=: dtype {t.dtype} != {dtype}")
+    if t.device != device:
+        raise ValueError(f"{name}=: device {t.device} != {device}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}=: must be contiguous")
+    return t
+
+
+def _check_ws(ws, nbytes, device, name="workspace"):
+    if not isinstance(ws, torch.Tensor) or ws.device != device or not ws.is_contiguous():
+        raise ValueError(f"{name}=: expected a contiguous tensor on {device}")
+    if ws.numel() * ws.element_size() < nbytes:
+        raise ValueError(f"{name} has {ws.numel() * ws.element_size()} bytes, need {nbytes}")
+    if ws.data_ptr() % 16:
+        raise ValueError(f"{name}=: must be 16-byte aligned")
+    return ws
+
+
 def _flags(leaky=False, reciprocal=False, atomic=False):
     return ((_lib.FLAG_LEAKY_RELU if leaky else 0) | (_lib.FLAG_COORD_RECIPROCAL if reciprocal else 0)
             | (_lib.FLAG_WARP_BWD_ATOMIC if atomic else 0))
@@ -54,6 +82,7 @@ def corr_fwd(x1, x2, leaky_slope=None, out=None):
     if x1.dtype != x2.dtype:
         raise ValueError(f"x1 is {x1.dtype} but x2 is {x2.dtype}")
     B, C, H, W = x1.shape
+    _check_out(out, (B, NUM_DISPLACEMENTS, H, W), x1.dtype, x1.device, "out")
     if x1.numel() == 0:  # empty batch: the reference returns an empty cost volume too
         return x1.new_empty((B, NUM_DISPLACEMENTS, H, W)) if out is None else out
     if x1.dtype == torch.bfloat16 and B * H * W > BF16_NATIVE_MAX_PIXELS and W % 8 != 0:
@@ -83,6 +112,10 @@ def corr_bwd(x1, x2, gout, need_gx1=True, need_gx2=True, gx1=None, gx2=None):
         raise ValueError(f"grad_output.shape {tuple(gout.shape)} != {(B, NUM_DISPLACEMENTS, H, W)}")
     if not (x1.dtype == x2.dtype == gout.dtype):
         raise ValueError(f"dtype mismatch: {x1.dtype}, {x2.dtype}, {gout.dtype}")
+    if gout.device != x1.device:
+        raise RuntimeError("x1 and grad_output are on different devices")
+    _check_out(gx1, x1.shape, x1.dtype, x1.device, "gx1")
+    _check_out(gx2, x2.shape, x2.dtype, x2.device, "gx2")
     if x1.numel() == 0:
         return (torch.empty_like(x1) if need_gx1 else None, torch.empty_like(x2) if need_gx2 else None)
     if x1.dtype == torch.bfloat16 and B * H * W > BF16_NATIVE_MAX_PIXELS and W % 8 != 0:
@@ -135,6 +168,7 @@ def warp_fwd(x, flow, pad="border", reciprocal=False, out=None):
     B, C, H, W = x.shape
     if H < 2 or W < 2:
         raise ValueError("flow_warp needs H, W >= 2 (the reference divides by size-1)")
+    _check_out(out, x.shape, x.dtype, x.device, "out")
     if out is None:
         out = torch.empty_like(x)
     if x.numel() == 0:
@@ -161,6 +195,8 @@ def warp_bwd(x, flow, gout, pad="border", need_gx=True, need_gflow=True, recipro
         raise ValueError(f"x is {x.dtype} but grad_output is {gout.dtype}")
     flow = _flow(flow, x)
     B, C, H, W = x.shape
+    _check_out(gx, x.shape, x.dtype, x.device, "gx")
+    _check_out(gflow, flow.shape, torch.float32, x.device, "gflow")
     if x.numel() == 0:
         return (torch.empty_like(x) if need_gx else None, torch.empty_like(flow) if need_gflow else None)
     flags = _flags(reciprocal=reciprocal, atomic=atomic)
@@ -173,8 +209,7 @@ def warp_bwd(x, flow, gout, pad="border", need_gx=True, need_gflow=True, recipro
         ws_bytes = L.usf_warp_bwd_workspace_bytes(B, C, H, W, flags)
         if ws_bytes:
             ws = workspace if workspace is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-            if ws.numel() * ws.element_size() < ws_bytes:
-                raise ValueError(f"workspace has {ws.numel() * ws.element_size()} bytes, need {ws_bytes}")
+            _check_ws(ws, ws_bytes, x.device)
     with torch.cuda.device(x.device):
         st = L.usf_warp_bwd(x.data_ptr(), flow.data_ptr(), gout.data_ptr(),
                             gx.data_ptr() if need_gx else None, gflow.data_ptr() if need_gflow else None,
@@ -201,6 +236,7 @@ def occ_bidirection(flow12, flow21, scale=0.01, bias=0.5, reciprocal=False, out=
     B, _, H, W = flow12.shape
     if H < 2 or W < 2:
         raise ValueError("get_occu_mask_bidirection needs H, W >= 2 (flow_warp divides by size-1)")
+    _check_out(out, (B, 1, H, W), torch.float32, flow12.device, "out")
     if out is None:
         out = torch.empty((B, 1, H, W), dtype=torch.float32, device=flow12.device)
     if flow12.numel() == 0:
@@ -223,6 +259,7 @@ def occ_backward(flow21, th=0.2, want_range_map=False, out=None, workspace=None)
     L = _lib.load()
     flow21 = _flow_pair(flow21, "flow21")
     B, _, H, W = flow21.shape
+    _check_out(out, (B, 1, H, W), torch.float32, flow21.device, "out")
     if out is None:
         out = torch.empty((B, 1, H, W), dtype=torch.float32, device=flow21.device)
     rng = torch.empty_like(out) if want_range_map else None
@@ -230,8 +267,7 @@ def occ_backward(flow21, th=0.2, want_range_map=False, out=None, workspace=None)
         return (out, rng) if want_range_map else out
     ws_bytes = L.usf_occ_backward_workspace_bytes(B, H, W)
     ws = workspace if workspace is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=flow21.device)
-    if ws.numel() * ws.element_size() < ws_bytes:
-        raise ValueError(f"workspace has {ws.numel() * ws.element_size()} bytes, need {ws_bytes}")
+    _check_ws(ws, ws_bytes, flow21.device)
     with torch.cuda.device(flow21.device):
         st = L.usf_occ_backward(flow21.data_ptr(), out.data_ptr(), rng.data_ptr() if want_range_map else None,
                                 B, H, W, float(th), ws.data_ptr(), ws_bytes, _stream(flow21))

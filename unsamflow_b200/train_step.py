@@ -17,7 +17,8 @@ from .pwclite import PWCLite
 
 
 class TrainStep:
-    def __init__(self, batch, height, width, device, seed=42, batch_directions=False, ddp=False, lr=2e-4):
+    def __init__(self, batch, height, width, device, seed=42, batch_directions=False, ddp=False, lr=2e-4,
+                 weight_decay=1e-6, bias_decay=0.0):
         torch.manual_seed(seed)
         self.device = torch.device(device)
         self.model = PWCLite(batch_directions=batch_directions).to(self.device)
@@ -28,7 +29,17 @@ class TrainStep:
                 self.model, device_ids=[self.device.index] if self.device.type == "cuda" else None,
                 bucket_cap_mb=16, gradient_as_bucket_view=True, static_graph=True)
         self.loss_fn = UnFlowLoss()
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-7)
+        # trainer/base_trainer.py:140-165 with configs/kitti_base.json: Adam(lr 2e-4, betas (0.9, 0.999), eps 1e-7)
+        # over two parameter groups -- weights with weight_decay 1e-6, biases with bias_decay 0
+        # (utils/torch_utils.py:27-41: ".weight" / ".bias" in the parameter name, everything else undecayed)
+        named = list(self.model.named_parameters())
+        weights = [p for n, p in named if ".weight" in n]
+        biases = [p for n, p in named if ".bias" in n]
+        others = [p for n, p in named if ".weight" not in n and ".bias" not in n]
+        groups = [{"params": biases, "weight_decay": bias_decay}, {"params": weights, "weight_decay": weight_decay}]
+        if others:
+            groups.append({"params": others, "weight_decay": 0.0})
+        self.opt = torch.optim.Adam(groups, lr=lr, betas=(0.9, 0.999), eps=1e-7)
         gen = torch.Generator().manual_seed(seed + (dist.get_rank() if ddp else 0))
         self.img1 = torch.rand(batch, 3, height, width, generator=gen).to(self.device)
         self.img2 = torch.rand(batch, 3, height, width, generator=gen).to(self.device)
