@@ -47,7 +47,7 @@
 extern "C" {
 #endif
 
-#define USF_ABI_VERSION 2
+#define USF_ABI_VERSION 3
 
 typedef enum usf_status {
     USF_OK = 0,
@@ -55,7 +55,7 @@ typedef enum usf_status {
     USF_ERR_BAD_ARG = -2,     /* null pointer, unknown dtype / pad mode / flag, md != 4 */
     USF_ERR_WORKSPACE = -3,   /* workspace missing, misaligned or smaller than usf_*_workspace_bytes */
     USF_ERR_CUDA = -4,        /* a CUDA runtime call failed; see usf_last_cuda_error() */
-    USF_ERR_UNSUPPORTED = -5  /* valid request this build does not implement (none at ABI version 2) */
+    USF_ERR_UNSUPPORTED = -5  /* valid request this build does not implement (none at ABI version 3) */
 } usf_status;
 
 /* storage type of feature tensors; arithmetic is fp32 either way (bf16: one rounding per output element) */
@@ -77,6 +77,11 @@ typedef enum usf_pad { USF_PAD_BORDER = 0, USF_PAD_ZEROS = 1 } usf_pad;
 /* warp bwd: accumulate gx with global float atomics (red.global.add.f32, what ATen
  * does) instead of the default atomic-free tap-list gather.  For A/B measurements. */
 #define USF_FLAG_WARP_BWD_ATOMIC 4u
+/* warp bwd: the caller guarantees that the first usf_warp_bwd_workspace_clean_bytes() bytes of
+ * `workspace` are zero -- after a one-time memset, or after any earlier usf_warp_bwd call on the
+ * same workspace, which always leaves them zeroed -- so the per-call memset node is skipped.
+ * For callers that keep one workspace per call site alive across steps (CUDA-graph replays). */
+#define USF_FLAG_WORKSPACE_CLEAN 8u
 
 int usf_abi_version(void);
 const char *usf_status_string(int status);
@@ -123,6 +128,9 @@ int usf_warp_fwd(const void *x, const float *flow, void *out, int B, int C, int 
  * then be NULL).  Contents need no initialisation; the pointer passed to usf_warp_bwd
  * must be 16-byte aligned. */
 size_t usf_warp_bwd_workspace_bytes(int B, int C, int H, int W, unsigned flags);
+/* Leading bytes of that workspace that hold the tap counters (see USF_FLAG_WORKSPACE_CLEAN); 0 when
+ * no workspace is needed. */
+size_t usf_warp_bwd_workspace_clean_bytes(int B, int C, int H, int W, unsigned flags);
 
 /*
  * Gradients of the backward warp.  gout: [B,C,H,W].  gx: [B,C,H,W] or NULL;

@@ -27,14 +27,14 @@ def declared_symbols():
 def test_header_symbols_are_exported(lib):
     from unsamflow_b200 import _lib
     names = declared_symbols()
-    assert len(names) == 13
+    assert len(names) == 14
     assert sorted(_lib.SYMBOLS) == names
     for n in names:
         assert getattr(lib, n) is not None
 
 
 def test_abi_version_and_status_strings(lib):
-    assert lib.usf_abi_version() == 2
+    assert lib.usf_abi_version() == 3
     for st in (0, -1, -2, -3, -4, -5):
         assert lib.usf_status_string(st)
     assert b"unknown" in lib.usf_status_string(-99)
@@ -69,6 +69,11 @@ def test_argument_validation_without_a_gpu(lib):
     # ... smaller ones run as one kernel with shared-memory tap lists: no workspace
     assert lib.usf_warp_bwd_workspace_bytes(8, 96, 16, 52, 0) == 0
     assert lib.usf_warp_bwd_workspace_bytes(1, 1, 32, 32, 0) == 0
+    # the counter region a USF_FLAG_WORKSPACE_CLEAN caller zeroes once: cnt (padded to 16 B) + 16
+    assert lib.usf_warp_bwd_workspace_clean_bytes(8, 32, 64, 208, 0) == 8 * 64 * 208 * 4 + 16
+    assert lib.usf_warp_bwd_workspace_clean_bytes(1, 1, 33, 33, 0) == 4368 + 16
+    assert lib.usf_warp_bwd_workspace_clean_bytes(8, 96, 16, 52, 0) == 0
+    assert lib.usf_warp_bwd_workspace_clean_bytes(1, 1, 40, 40, 4) == 0
     # occlusion masks: null pointers, unknown flag, H/W >= 2 for the warp inside, workspace size / alignment
     assert lib.usf_occ_bidirection(p, None, p, 1, 2, 2, 0.01, 0.5, 0, None) == BAD_ARG
     assert lib.usf_occ_bidirection(p, p, p, 1, 2, 2, 0.01, 0.5, 4, None) == BAD_ARG

@@ -249,6 +249,33 @@ def test_warp_bwd_collapse_overflows_tap_lists(usf):
         check(gf, ogf, f"gflow with overflow {H}x{W}")
 
 
+def test_warp_bwd_persistent_workspace_stays_clean(usf):
+    """USF_FLAG_WORKSPACE_CLEAN: a workspace zeroed once serves call after call without the per-call memset -- the
+    gather zeroes the tap counters it has read and its last CTA resets the overflow counters -- also right after a
+    call whose side list overflowed (collapse onto the border) and across different flows."""
+    from oracle import c_oracle
+    ops = usf.ops_mod
+    B, C, H, W = 2, 8, 40, 44
+    g = torch.Generator().manual_seed(21)
+    x, go = torch.randn(B, C, H, W, generator=g), torch.randn(B, C, H, W, generator=g)
+    collapse = torch.full((B, 2, H, W), 1000.0)
+    collapse[:, :, : H // 2] = torch.randn(B, 2, H // 2, W, generator=g) * 0.3 + 5.5
+    flows = [torch.randn(B, 2, H, W, generator=g), collapse, 4.0 * torch.randn(B, 2, H, W, generator=g), collapse,
+             torch.zeros(B, 2, H, W)]
+    ws = ops.warp_bwd_workspace(x.cuda())
+    nclean = ops._lib.load().usf_warp_bwd_workspace_clean_bytes(B, C, H, W, 0)
+    assert 0 < nclean < ws.numel()
+    for i, fl in enumerate(flows):
+        gx, gf = ops.warp_bwd(x.cuda(), fl.cuda(), go.cuda(), "border", workspace=ws, workspace_clean=True)
+        ogx, ogf = c_oracle.warp_bwd(x.numpy(), fl.numpy(), go.numpy(), "border")
+        check(gx, ogx, f"gx, call {i}")
+        check(gf, ogf, f"gflow, call {i}")
+        torch.cuda.synchronize()
+        assert int(ws[:nclean].max()) == 0, f"counters not left clean after call {i}"
+    with pytest.raises(ValueError):
+        ops.warp_bwd(x.cuda(), flows[0].cuda(), go.cuda(), workspace_clean=True)
+
+
 def test_warp_list_path_is_deterministic(usf):
     ops = usf.ops_mod
     g = torch.Generator().manual_seed(12)

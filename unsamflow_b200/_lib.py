@@ -10,18 +10,19 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 # USF_LIB_PATH overrides the library location (A/B runs against another build of the same ABI)
 LIB_PATH = os.environ.get("USF_LIB_PATH") or os.path.join(_PKG, "lib", "libunsamflow_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 F32, BF16 = 0, 1
 PAD_BORDER, PAD_ZEROS = 0, 1
 FLAG_LEAKY_RELU = 1
 FLAG_COORD_RECIPROCAL = 2
 FLAG_WARP_BWD_ATOMIC = 4
+FLAG_WORKSPACE_CLEAN = 8
 
 # every symbol include/unsamflow_b200.h declares (tests/test_abi.py checks header <-> library <-> this list)
 SYMBOLS = (
     "usf_abi_version", "usf_status_string", "usf_last_cuda_error", "usf_launch_count",
     "usf_reset_launch_count", "usf_corr_fwd", "usf_corr_bwd", "usf_warp_fwd",
-    "usf_warp_bwd_workspace_bytes", "usf_warp_bwd", "usf_occ_bidirection",
+    "usf_warp_bwd_workspace_bytes", "usf_warp_bwd_workspace_clean_bytes", "usf_warp_bwd", "usf_occ_bidirection",
     "usf_occ_backward_workspace_bytes", "usf_occ_backward",
 )
 
@@ -57,6 +58,8 @@ def load():
     L.usf_warp_fwd.argtypes = [vp, vp, vp, i, i, i, i, i, i, u, vp]
     L.usf_warp_bwd_workspace_bytes.restype = sz
     L.usf_warp_bwd_workspace_bytes.argtypes = [i, i, i, i, u]
+    L.usf_warp_bwd_workspace_clean_bytes.restype = sz
+    L.usf_warp_bwd_workspace_clean_bytes.argtypes = [i, i, i, i, u]
     L.usf_warp_bwd.restype = i
     L.usf_warp_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, u, vp, sz, vp]
     L.usf_occ_bidirection.restype = i

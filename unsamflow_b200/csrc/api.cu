@@ -17,6 +17,7 @@ int warp_fwd_f32(const float *, const float *, float *, int, int, int, int, int,
 int warp_bwd_f32(const float *, const float *, const float *, float *, float *, int, int, int, int, int,
                  unsigned, void *, size_t, cudaStream_t);
 size_t warp_bwd_workspace_bytes(int B, int H, int W);
+size_t warp_bwd_workspace_clean_bytes(int B, int H, int W);
 int corr_fwd_bf16(const void *, const void *, void *, int, int, int, int, unsigned, float, cudaStream_t);
 int corr_fwd_bf16_tiled(const void *, const void *, void *, int, int, int, int, unsigned, float, cudaStream_t);
 int corr_bwd_bf16(const void *, const void *, const void *, void *, void *, int, int, int, int, cudaStream_t);
@@ -198,12 +199,18 @@ size_t usf_warp_bwd_workspace_bytes(int B, int C, int H, int W, unsigned flags) 
     return warp_bwd_workspace_bytes(B, H, W);
 }
 
+size_t usf_warp_bwd_workspace_clean_bytes(int B, int C, int H, int W, unsigned flags) {
+    (void)C;
+    if (B <= 0 || H <= 0 || W <= 0 || (flags & USF_FLAG_WARP_BWD_ATOMIC)) return 0;
+    return warp_bwd_workspace_clean_bytes(B, H, W);
+}
+
 int usf_warp_bwd(const void *x, const float *flow, const void *gout, void *gx, float *gflow, int B, int C,
                  int H, int W, int pad_mode, int dtype, unsigned flags, void *workspace, size_t workspace_bytes,
                  void *stream) {
     if (!x || !flow || !gout) return USF_ERR_BAD_ARG;
     if (pad_mode != USF_PAD_BORDER && pad_mode != USF_PAD_ZEROS) return USF_ERR_BAD_ARG;
-    if (flags & ~(USF_FLAG_COORD_RECIPROCAL | USF_FLAG_WARP_BWD_ATOMIC)) return USF_ERR_BAD_ARG;
+    if (flags & ~(USF_FLAG_COORD_RECIPROCAL | USF_FLAG_WARP_BWD_ATOMIC | USF_FLAG_WORKSPACE_CLEAN)) return USF_ERR_BAD_ARG;
     if (int st = check_dims(B, C, H, W, 2)) return st;
     if (H < 2 || W < 2) return USF_ERR_BAD_SHAPE;
     if (!gx && !gflow) return USF_OK;

@@ -18,9 +18,9 @@
 //                       pairs (built once per call, channel independent, sorted by source so the
 //                       sum order is deterministic) and gathers  g_x[c,t] = sum_i w_i * gO[c,src_i]
 //                       with plain loads and one plain store: no float atomics, no zero-fill.
-//   warp_gx_overflow    targets hit by more than kSlots taps (e.g. a region clipped onto the image
-//                       border) keep their first kSlots taps in the list; the rest go through a
-//                       side list handled with float atomics after the gather has written g_x.
+//                       Targets hit by more than kSlots taps (e.g. a region clipped onto the image
+//                       border) keep their first kSlots taps in the list; the rest go through a side
+//                       list handled with float atomics (warp_gx_overflow) after the gather has written g_x.
 #include <stdlib.h>
 
 #include <map>
@@ -50,7 +50,7 @@ constexpr int kSlotsS = 16;  // ... in the shared-memory lists of the fused smal
 template <int NS, typename T, int CC = 0>
 __global__ void __launch_bounds__(kBlock, CC ? 6 : 5)
 warp_fwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, T *__restrict__ out, int N,
-                int Crt, int H, int W, int border, int rcp, FastDiv dHW, FastDiv dW) {
+                int Crt, int H, int W, int border, int rcp, FastDiv dHW, FastDiv dW, AxisK kx, AxisK ky) {
     pdl_wait();
     const int C = CC ? CC : Crt;
     constexpr int PPB = kBlock / NS;
@@ -74,7 +74,7 @@ warp_fwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, T *__re
             un = __ldg(flow + (size_t)bn * 2 * HW + remn);
             vn = __ldg(flow + (size_t)bn * 2 * HW + HW + remn);
         }
-        const Taps t = make_taps(y, xo, u, v, H, W, border, rcp);
+        const Taps t = make_taps_k((float)y, (float)xo, u, v, H, W, kx, ky, border, rcp);
         const float nw = t.ex * t.ey, ne = t.wx * t.ey, sw = t.ex * t.wy, se = t.wx * t.wy;
         // two row pointers (taps nw/ne and sw/se are neighbours) bumped by one slice stride per channel:
         // no per-tap address arithmetic in the loop; out-of-image taps are predicated off, never read
@@ -98,8 +98,10 @@ warp_fwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, T *__re
 
 // ---------------------------------------------------------------------------------------------
 // Workspace of the atomic-free g_x path, N = B*H*W target pixels:
-//   int   cnt[N]            taps received per target (zeroed by a memset node each call)
-//   int   ovf_n[4]          number of overflow taps (+ padding to 16 bytes)
+//   int   cnt[N]            taps received per target
+//   int   ovf_n[4]          [0] number of overflow taps, [1] CTAs of the gather that have finished
+//   (cnt and ovf_n must be zero when the tap kernel starts: a memset node per call, or -- with
+//   USF_FLAG_WORKSPACE_CLEAN -- the caller's promise; the gather leaves both zeroed again)
 //   int2  ent[N][kSlots]    (source pixel inside its image plane, weight bits)
 //   int   ovf_tgt[4N], ovf_src[4N]; float ovf_w[4N]     overflow side list (worst case: every tap)
 struct Workspace {
@@ -147,7 +149,7 @@ template <int NS, int MODE, typename T, int CC = 0>
 __global__ void __launch_bounds__(kBlock, (NS == 1 && !CC) ? 4 : 5)  // (5 would spill the generic single-slice form)
 warp_bwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, const T *__restrict__ gout,
                 T *__restrict__ gx, float *__restrict__ gflow, Workspace ws, int N, int Crt, int H, int W,
-                int border, int rcp, FastDiv dHW, FastDiv dW) {
+                int border, int rcp, FastDiv dHW, FastDiv dW, AxisK kx, AxisK ky) {
     pdl_wait();
     const int C = CC ? CC : Crt;  // see warp_fwd_kernel
     constexpr int PPB = kBlock / NS;
@@ -180,13 +182,19 @@ warp_bwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, const T
             b = dHW.div(p);
             rem = p - b * HW;
             const int y = dW.div(rem), xo = rem - y * W;
-            t = make_taps(y, xo, u, v, H, W, border, rcp);
+            t = make_taps_k((float)y, (float)xo, u, v, H, W, kx, ky, border, rcp);
             const float nw = t.ex * t.ey, ne = t.wx * t.ey, sw = t.ex * t.wy, se = t.wx * t.wy;
-            if (MODE == 1 && cs == 0) {
-                emit_tap(ws, b * HW, t.o_nw, t.k_nw, nw, rem);
-                emit_tap(ws, b * HW, t.o_ne, t.k_ne, ne, rem);
-                emit_tap(ws, b * HW, t.o_sw, t.k_sw, sw, rem);
-                emit_tap(ws, b * HW, t.o_se, t.k_se, se, rem);
+            if (MODE == 1) {
+                // every slice has computed the same taps: spread the four list appends (an atomic with a
+                // dependent store each) over up to four slices instead of leaving them all to slice 0 while the
+                // others wait at the barrier below (a third of this kernel's stall samples, ncu)
+                constexpr int EM = NS >= 4 ? 4 : NS;  // emitting slices
+                if (cs < EM) {
+                    if (cs == 0) emit_tap(ws, b * HW, t.o_nw, t.k_nw, nw, rem);
+                    if (cs == 1 % EM) emit_tap(ws, b * HW, t.o_ne, t.k_ne, ne, rem);
+                    if (cs == 2 % EM) emit_tap(ws, b * HW, t.o_sw, t.k_sw, sw, rem);
+                    if (cs == 3 % EM) emit_tap(ws, b * HW, t.o_se, t.k_se, se, rem);
+                }
             }
             const size_t step = (size_t)NS * HW;
             const T *gb = gout + ((size_t)b * C + cs) * HW + rem;
@@ -235,10 +243,9 @@ warp_bwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, const T
         }
         if (writer) {
             // grid_sampler backward: ggrid = mult * gi; norm_grid backward: (g / (size-1)) * 2
-            const float sx = (float)(W - 1), sy = (float)(H - 1);
             const float gxn = __fmul_rn(t.mx, gix), gyn = __fmul_rn(t.my, giy);
-            const float dfx = rcp ? __fmul_rn(gxn, __fdiv_rn(1.0f, sx)) : __fdiv_rn(gxn, sx);
-            const float dfy = rcp ? __fmul_rn(gyn, __fdiv_rn(1.0f, sy)) : __fdiv_rn(gyn, sy);
+            const float dfx = rcp ? __fmul_rn(gxn, kx.rcp) : div_by_size(gxn, kx);
+            const float dfy = rcp ? __fmul_rn(gyn, ky.rcp) : div_by_size(gyn, ky);
             gflow[(size_t)b * 2 * HW + rem] = __fmul_rn(dfx, 2.0f);
             gflow[(size_t)b * 2 * HW + HW + rem] = __fmul_rn(dfy, 2.0f);
         }
@@ -275,6 +282,7 @@ warp_gx_gather(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, int
         const int4 *e4 = reinterpret_cast<const int4 *>(ws.ent + (size_t)(live ? p : 0) * kSlots);
         const int4 e01 = e4[0], e23 = e4[1];
         n = live ? min(ws.cnt[p], kSlots) : 0;
+        if (live) ws.cnt[p] = 0;  // leave the counters clean for the next call on this workspace
 #pragma unroll
         for (int i = 0; i < kSlots / 2; ++i) {
             int4 e = i == 0 ? e01 : (i == 1 ? e23 : make_int4(0, 0, 0, 0));
@@ -314,25 +322,26 @@ warp_gx_gather(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, int
             }
         }
     }
-    if (!live) return;
-    const int b = dHW.div(p), rem = p - b * HW;
-    const size_t step = (size_t)NS * HW;
-    const T *plane = gout + ((size_t)b * C + cs) * HW;
-    T *o = gx + ((size_t)b * C + cs) * HW + rem;
-    // most targets receive <= 4 taps (exactly 4 for a smooth flow): the upper half is a rarely taken branch
-    // (unroll 8 here costs registers and occupancy: measured 37 -> 46 us at 8x32x64x208)
+    if (live) {
+        const int b = dHW.div(p), rem = p - b * HW;
+        const size_t step = (size_t)NS * HW;
+        const T *plane = gout + ((size_t)b * C + cs) * HW;
+        T *o = gx + ((size_t)b * C + cs) * HW + rem;
+        // most targets receive <= 4 taps (exactly 4 for a smooth flow): the upper half is a rarely taken branch
+        // (unroll 8 here costs registers and occupancy: measured 37 -> 46 us at 8x32x64x208)
 #pragma unroll 4
-    for (int c = cs; c < C; c += NS, plane += step, o += step) {
-        float acc = 0.f;
+        for (int c = cs; c < C; c += NS, plane += step, o += step) {
+            float acc = 0.f;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (i < n) acc = fmaf(w[i], ldf(plane + src[i]), acc);
-        if (n > 4) {
-#pragma unroll
-            for (int i = 4; i < kSlots; ++i)
+            for (int i = 0; i < 4; ++i)
                 if (i < n) acc = fmaf(w[i], ldf(plane + src[i]), acc);
+            if (n > 4) {
+#pragma unroll
+                for (int i = 4; i < kSlots; ++i)
+                    if (i < n) acc = fmaf(w[i], ldf(plane + src[i]), acc);
+            }
+            stf(o, acc);
         }
-        stf(o, acc);
     }
 }
 
@@ -349,7 +358,7 @@ template <int NS, typename T>
 __global__ void __launch_bounds__(kBlock)
 warp_bwd_small(const T *__restrict__ x, const float *__restrict__ flow, const T *__restrict__ gout,
                T *__restrict__ gx, float *__restrict__ gflow, int C, int H, int W, int border, int rcp,
-               FastDiv dW, FastDiv dBpi) {
+               FastDiv dW, FastDiv dBpi, AxisK kx, AxisK ky) {
     pdl_wait();
     constexpr int PPB = kBlock / NS;
     extern __shared__ __align__(16) int sm_i[];
@@ -380,7 +389,7 @@ warp_bwd_small(const T *__restrict__ x, const float *__restrict__ flow, const T 
         const int src = tid + k4 * kBlock;
         if (src >= HW) break;
         const int y = dW.div(src), xo = src - y * W;
-        const Taps t = make_taps(y, xo, fu[k4], fv[k4], H, W, border, rcp);
+        const Taps t = make_taps_k((float)y, (float)xo, fu[k4], fv[k4], H, W, kx, ky, border, rcp);
         const int off[4] = {t.o_nw, t.o_ne, t.o_sw, t.o_se};
         const bool ok[4] = {t.k_nw, t.k_ne, t.k_sw, t.k_se};
         const float wt[4] = {t.ex * t.ey, t.wx * t.ey, t.ex * t.wy, t.wx * t.wy};
@@ -412,7 +421,7 @@ warp_bwd_small(const T *__restrict__ x, const float *__restrict__ flow, const T 
     Taps t;
     if (live && gflow != nullptr) {
         const int y = dW.div(rem), xo = rem - y * W;
-        t = make_taps(y, xo, __ldg(fl + rem), __ldg(fl + HW + rem), H, W, border, rcp);
+        t = make_taps_k((float)y, (float)xo, __ldg(fl + rem), __ldg(fl + HW + rem), H, W, kx, ky, border, rcp);
         const T *gb = gout + ((size_t)b * C + cs) * HW + rem;
         const T *p0 = x + ((size_t)b * C + cs) * HW + t.o_nw;
         const T *p1 = p0 + W;
@@ -481,10 +490,9 @@ warp_bwd_small(const T *__restrict__ x, const float *__restrict__ flow, const T 
             gix += red[s2 * PPB + pl];
             giy += red[kBlock + s2 * PPB + pl];
         }
-        const float sx = (float)(W - 1), sy = (float)(H - 1);
         const float gxn = __fmul_rn(t.mx, gix), gyn = __fmul_rn(t.my, giy);
-        const float dfx = rcp ? __fmul_rn(gxn, __fdiv_rn(1.0f, sx)) : __fdiv_rn(gxn, sx);
-        const float dfy = rcp ? __fmul_rn(gyn, __fdiv_rn(1.0f, sy)) : __fdiv_rn(gyn, sy);
+        const float dfx = rcp ? __fmul_rn(gxn, kx.rcp) : div_by_size(gxn, kx);
+        const float dfy = rcp ? __fmul_rn(gyn, ky.rcp) : div_by_size(gyn, ky);
         gflow[(size_t)b * 2 * HW + rem] = __fmul_rn(dfx, 2.0f);
         gflow[(size_t)b * 2 * HW + HW + rem] = __fmul_rn(dfy, 2.0f);
     }
@@ -520,10 +528,15 @@ warp_bwd_small(const T *__restrict__ x, const float *__restrict__ flow, const T 
     }
 }
 
+// Overflow side list: normally short, but NOT normally empty -- a flow that leaves the image is clipped onto the
+// border, and a border pixel easily collects more than kSlots taps (the bench's 3-px flows put ~17 k entries here at
+// 8x64x208).  Parallel over entries x channels; folding this pass into the gather's last CTA was tried and cost
+// 150 us at that size.  The last CTA to finish resets the counters (USF_FLAG_WORKSPACE_CLEAN contract).
 template <typename T>
 __global__ void __launch_bounds__(kBlock)
 warp_gx_overflow(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, int cap, int C, int HW) {
     pdl_wait();
+    __shared__ int s_last;
     const int n = min(ws.ovf_n[0], cap);
     const long total = (long)n * C;
     for (long it = (long)blockIdx.x * kBlock + threadIdx.x; it < total; it += (long)gridDim.x * kBlock) {
@@ -532,6 +545,13 @@ warp_gx_overflow(const T *__restrict__ gout, T *__restrict__ gx, Workspace ws, i
         const int b = tgt / HW, trem = tgt - b * HW;
         const size_t plane = ((size_t)b * C + c) * HW;
         atomic_addf(gx + plane + trem, ws.ovf_w[j] * ldf(gout + plane + ws.ovf_src[j]));
+    }
+    __syncthreads();  // every thread of this CTA has read ovf_n[0]
+    if (threadIdx.x == 0) s_last = atomicAdd(ws.ovf_n + 1, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        ws.ovf_n[0] = 0;
+        ws.ovf_n[1] = 0;
     }
 }
 
@@ -560,6 +580,10 @@ int pick_ns(int C, int N) {
 size_t warp_bwd_workspace_bytes(int B, int H, int W) {
     return (long)H * W <= kWarpSmallMaxHW ? 0 : ws_bytes((size_t)B * H * W);
 }
+// the tap counters at the head of the workspace (what the per-call memset covers)
+size_t warp_bwd_workspace_clean_bytes(int B, int H, int W) {
+    return (long)H * W <= kWarpSmallMaxHW ? 0 : cnt_bytes((size_t)B * H * W) + 16;
+}
 
 // CTAs of `kernel` that fit on the device at once (cached per kernel and device)
 static int resident_ctas(const void *kernel) {
@@ -586,12 +610,12 @@ static int warp_fwd_t(const T *x, const float *flow, T *out, int B, int C, int H
 #define USF_LAUNCH(NS)                                                                      \
     {                                                                                       \
         const int res = resident_ctas((const void *)warp_fwd_kernel<NS, T>);                \
-        usf_launch((warp_fwd_kernel<NS, T>), dim3(blocks < res ? blocks : res), dim3(kBlock), 0, stream, x, flow, out, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W)); \
+        usf_launch((warp_fwd_kernel<NS, T>), dim3(blocks < res ? blocks : res), dim3(kBlock), 0, stream, x, flow, out, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W), make_axis(W), make_axis(H)); \
     }
     if (ns == 1 && C == 3) {  // loss-side warp of an RGB image
         const int res = resident_ctas((const void *)warp_fwd_kernel<1, T, 3>);
         usf_launch((warp_fwd_kernel<1, T, 3>), dim3(blocks < res ? blocks : res), dim3(kBlock), 0, stream, 
-            x, flow, out, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W));
+            x, flow, out, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W), make_axis(W), make_axis(H));
         return note_launch(cudaGetLastError());
     }
     switch (ns) {
@@ -613,7 +637,7 @@ static cudaError_t launch_bwd(int ns, int blocks, const T *x, const float *flow,
     {                                                                                                           \
         const int res = resident_ctas((const void *)warp_bwd_kernel<NS, MODE, T>);                              \
         usf_launch((warp_bwd_kernel<NS, MODE, T>), dim3(blocks < res ? blocks : res), dim3(kBlock), 0, stream,                        \
-            x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W));       \
+            x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W), make_axis(W), make_axis(H)); \
     }
     switch (ns) {
         case 32: USF_LAUNCH(32); break;
@@ -639,7 +663,7 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
         if (ns == 1 && C == 3) {  // loss-side warp of an RGB image: gradient wrt the flow only
             const int res = resident_ctas((const void *)warp_bwd_kernel<1, 0, T, 3>);
             usf_launch((warp_bwd_kernel<1, 0, T, 3>), dim3(blocks < res ? blocks : res), dim3(kBlock), 0, stream, 
-                x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W));
+                x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W), make_axis(W), make_axis(H));
             return note_launch(cudaGetLastError());
         }
         return note_launch(launch_bwd<0, T>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
@@ -656,7 +680,7 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
 #define USF_LAUNCH(NS)                                                                                       \
     if ((e = ensure_smem((const void *)warp_bwd_small<NS, T>, (int)smem)) == cudaSuccess)                    \
         usf_launch((warp_bwd_small<NS, T>), dim3(B * bpi), dim3(kBlock), smem, stream, x, flow, gout, gx, gflow, C, H, W, border, rcp, \
-                                                                 make_fastdiv(W), make_fastdiv(bpi));
+                                                                 make_fastdiv(W), make_fastdiv(bpi), make_axis(W), make_axis(H));
         switch (ns) {
             case 32: USF_LAUNCH(32); break;
             case 16: USF_LAUNCH(16); break;
@@ -671,8 +695,10 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
     if (workspace == nullptr || workspace_bytes < ws_bytes((size_t)N) || ((uintptr_t)workspace & 15))
         return USF_ERR_WORKSPACE;
     ws = carve(workspace, (size_t)N);
-    cudaError_t e = cudaMemsetAsync(ws.cnt, 0, cnt_bytes((size_t)N) + 16, stream);
-    if (e != cudaSuccess) { note_cuda_error(e); return USF_ERR_CUDA; }
+    if (!(flags & USF_FLAG_WORKSPACE_CLEAN)) {  // counters must start at zero; the gather zeroes them again
+        cudaError_t e = cudaMemsetAsync(ws.cnt, 0, cnt_bytes((size_t)N) + 16, stream);
+        if (e != cudaSuccess) { note_cuda_error(e); return USF_ERR_CUDA; }
+    }
     int st = note_launch(launch_bwd<1, T>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
     if (st != USF_OK) return st;
 #define USF_LAUNCH(NS) usf_launch((warp_gx_gather<NS, T>), dim3(blocks), dim3(kBlock), 0, stream, gout, gx, ws, N, C, HW, make_fastdiv(HW))
@@ -688,7 +714,7 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
     st = note_launch(cudaGetLastError());
     if (st != USF_OK) return st;
     // fixed grid (the entry count lives on the device), sized for the worst case of this shape: up to 2 CTAs
-    // per SM (the list is normally empty or short), grid-stride over entries x channels
+    // per SM (the list is normally short), grid-stride over entries x channels
     long ovf_blocks = ((long)4 * N * C + 16L * kBlock - 1) / (16L * kBlock);
     ovf_blocks = ovf_blocks < 16 ? 16 : (ovf_blocks > sm_count() * 2 ? sm_count() * 2 : ovf_blocks);
     usf_launch(warp_gx_overflow<T>, dim3((int)ovf_blocks), dim3(kBlock), 0, stream, gout, gx, ws, 4 * N, C, HW);

@@ -135,8 +135,8 @@ class HotPathStep:
                     t[f"x2w.L{lvl}.{d}"] = torch.empty(B, C, h, w, device=self.device)
                     t[f"gfeat2.L{lvl}.{d}"] = torch.empty(B, C, h, w, device=self.device)
                     t[f"gflow.L{lvl}.{d}"] = torch.empty(B, 2, h, w, device=self.device)
-                    t[f"ws.L{lvl}.{d}"] = torch.empty(
-                        ops.warp_bwd_workspace_bytes(t[f"f1.L{lvl}"]), dtype=torch.uint8, device=self.device)
+                    # persistent per call site: counters zeroed once here, left zeroed by every call
+                    t[f"ws.L{lvl}.{d}"] = ops.warp_bwd_workspace(t[f"f1.L{lvl}"])
                     self.input_names.append(f"flow.L{lvl}.{d}")
                 t[f"corr.L{lvl}.{d}"] = torch.empty(B, K, h, w, device=self.device)
                 t[f"gcorr.L{lvl}.{d}"] = randn(B, K, h, w)
@@ -181,8 +181,9 @@ class HotPathStep:
                     gf2, gfl, ws = t[f"gfeat2.L{lvl}.{d}"], t[f"gflow.L{lvl}.{d}"], t[f"ws.L{lvl}.{d}"]
                     bwd.append(OpRecord(f"warp_bwd.L{lvl}.{d}", "warp_bwd",
                                         (lambda x2=x2, fl=fl, g2=g2, gf2=gf2, gfl=gfl, ws=ws:
-                                         ops.warp_bwd(x2, fl, g2, pad, gx=gf2, gflow=gfl, workspace=ws)),
-                                        warp_bwd_bytes(*shp), launches=3, shape=shp))
+                                         ops.warp_bwd(x2, fl, g2, pad, gx=gf2, gflow=gfl, workspace=ws,
+                                                      workspace_clean=True)),
+                                        warp_bwd_bytes(*shp), launches=2, shape=shp))
                 bwd.append(OpRecord(f"corr_bwd.L{lvl}.{d}", "corr_bwd",
                                     (lambda x1=x1, x2w=x2w, go=go, g1=g1, g2=g2:
                                      ops.corr_bwd(x1, x2w, go, gx1=g1, gx2=g2)),

@@ -69,9 +69,9 @@ def _check_ws(ws, nbytes, device, name="workspace"):
     return ws
 
 
-def _flags(leaky=False, reciprocal=False, atomic=False):
+def _flags(leaky=False, reciprocal=False, atomic=False, ws_clean=False):
     return ((_lib.FLAG_LEAKY_RELU if leaky else 0) | (_lib.FLAG_COORD_RECIPROCAL if reciprocal else 0)
-            | (_lib.FLAG_WARP_BWD_ATOMIC if atomic else 0))
+            | (_lib.FLAG_WARP_BWD_ATOMIC if atomic else 0) | (_lib.FLAG_WORKSPACE_CLEAN if ws_clean else 0))
 
 
 def corr_fwd(x1, x2, leaky_slope=None, out=None):
@@ -185,9 +185,22 @@ def warp_bwd_workspace_bytes(x, atomic=False):
     return int(_lib.load().usf_warp_bwd_workspace_bytes(B, C, H, W, _flags(atomic=atomic)))
 
 
+def warp_bwd_workspace(x, atomic=False):
+    """A persistent workspace for warp_bwd(..., workspace=ws, workspace_clean=True): allocated once per call site
+    with its counter region zeroed; every warp_bwd call leaves it zeroed again (usf_warp_bwd_workspace_clean_bytes),
+    so the per-call memset disappears from the step.  One workspace serves one call at a time."""
+    B, C, H, W = x.shape
+    L = _lib.load()
+    flags = _flags(atomic=atomic)
+    ws = torch.empty(int(L.usf_warp_bwd_workspace_bytes(B, C, H, W, flags)), dtype=torch.uint8, device=x.device)
+    ws[:int(L.usf_warp_bwd_workspace_clean_bytes(B, C, H, W, flags))].zero_()
+    return ws
+
+
 def warp_bwd(x, flow, gout, pad="border", need_gx=True, need_gflow=True, reciprocal=False, atomic=False,
-             gx=None, gflow=None, workspace=None):
-    """-> (gx, gflow); gx= / gflow= / workspace= (uint8 tensor) may be preallocated."""
+             gx=None, gflow=None, workspace=None, workspace_clean=False):
+    """-> (gx, gflow); gx= / gflow= / workspace= (uint8 tensor) may be preallocated.  workspace_clean=True:
+    `workspace` came from warp_bwd_workspace() (counters zero on entry, left zero on exit)."""
     L = _lib.load()
     x, gout = _feat(x, "x"), _feat(gout, "grad_output")
     _same(x, gout, "x", "grad_output")
@@ -199,7 +212,9 @@ def warp_bwd(x, flow, gout, pad="border", need_gx=True, need_gflow=True, recipro
     _check_out(gflow, flow.shape, torch.float32, x.device, "gflow")
     if x.numel() == 0:
         return (torch.empty_like(x) if need_gx else None, torch.empty_like(flow) if need_gflow else None)
-    flags = _flags(reciprocal=reciprocal, atomic=atomic)
+    if workspace_clean and workspace is None:
+        raise ValueError("workspace_clean=True needs the persistent workspace= it refers to")
+    flags = _flags(reciprocal=reciprocal, atomic=atomic, ws_clean=workspace_clean)
     if need_gx and gx is None:
         gx = torch.empty_like(x)
     if need_gflow and gflow is None:
