@@ -33,6 +33,10 @@ cudaError_t ensure_smem(const void *kernel, int smem_bytes);
 bool pdl_enabled();  // api.cu
 // SMs of the current device (cudaDevAttrMultiProcessorCount, cached per device; 148 on B200): grid sizing
 int sm_count();      // api.cu
+// Tried in round 2 and dropped: griddepcontrol.launch_dependents right after the wait (the next kernel's CTAs are
+// then dispatched into freed SM slots and sit in their own wait while this grid drains).  Safe by construction --
+// every kernel's first statement is the wait -- but the step got 3 % slower (0.598 -> 0.614 ms): the parked CTAs hold
+// registers and shared memory that the two concurrently running direction streams would otherwise use.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
 template <typename... KArgs, typename... Args>
 inline cudaError_t usf_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
