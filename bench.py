@@ -6,13 +6,14 @@ synthetic 256x832 pairs, B=8, 1 B200" restricted to the path this repo owns: eve
 and flow_warp call of one training iteration, forward and backward (unsamflow_b200/hotpath.py:
 10 corr fwd + 10 corr bwd + 16 warp fwd + 16 warp bwd), on seeded synthetic tensors.
 
-  value      pairs/s with all inputs resident in HBM; a step = CUDA graph A -> the dominant op launched
-             eagerly between two CUDA events -> CUDA graph B.  L2 is flushed between steps (outside
-             the per-step event pair).  Device time from CUDA events, max over ranks.
+  value      pairs/s with all inputs resident in HBM; a step = one CUDA graph (both flow directions on two
+             streams inside it).  L2 is flushed between steps (outside the per-step event pair).  Device
+             time from CUDA events, max over ranks.
   e2e        same step through the public tensor API with HOST inputs: H2D of every input from pinned
              memory and D2H of the step's results are inside the timed region.
-  roofline   the dominant op's kernel: algorithmic bytes per launch / mean launch duration (events
-             inside the timed region) against MEASURED_PEAKS.json.
+  roofline   the dominant op's kernel: algorithmic bytes per launch / mean launch duration (external
+             timing events recorded inside the graph around that kernel, on its stream, in every timed
+             step) against MEASURED_PEAKS.json.
   cpu_baseline / --impl reference
              the reference's CPU path (oracle/torch_port.py: the same ATen calls the reference
              makes) on the host cores, on a bounded sample (1 pair per step).
@@ -308,10 +309,12 @@ def run_ours(args):
         with open(args.op_table, "w") as f:
             json.dump(table, f, indent=1)
 
-    # ---- graphs: A (before the dominant op), eager dominant op, B (after) ----------------------------
-    # --streams 2 (default): the two flow directions run on two streams inside graphs A and B (the
-    # reference calls its two decoders back to back although they are independent, pwclite.py:430-432);
-    # the dominant op always runs alone between the two events, so its duration is a kernel time.
+    # ---- the step: ONE CUDA graph, the two flow directions on two streams inside it (the reference calls its two
+    # decoders back to back although they are independent, pwclite.py:430-432; --streams 1 serialises them).  The
+    # dominant op's kernel is timed where it runs: two external timing events recorded inside the graph on the
+    # kernel's own stream, around its launch (CUDA allows event-record nodes with cudaEventRecordExternal in a
+    # capture), read after every replay.  If this torch cannot record external events during capture, the step
+    # falls back to round 1's form: graph A -> the dominant op launched eagerly between two events -> graph B.
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -319,50 +322,92 @@ def run_ours(args):
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     if args.streams == 2:
+        step.run_concurrent(step.chains)  # warm the side streams up
+        torch.cuda.synchronize()
+    run_full = (lambda: step.run_concurrent(step.chains)) if args.streams == 2 else step.run
+    gMarked = None
+    step_form = ("one CUDA graph per step (value, ms_per_step); dominant kernel timed in place by external events "
+                 "inside that graph, and alone -- graph A -> kernel between two events -> graph B -- in a second loop")
+    k0 = k1 = None
+    try:
+        k0 = torch.cuda.Event(enable_timing=True, external=True)
+        k1 = torch.cuda.Event(enable_timing=True, external=True)
+        step.marks = {dom.name: (k0, k1)}
+        if args.streams != 2:  # single stream: step.run() has no hook, wrap the op itself
+            base_fn = dom.fn
+
+            def marked_fn():
+                k0.record()
+                base_fn()
+                k1.record()
+            dom.fn = marked_fn
+        gMarked = capture(run_full)
+        gMarked.replay()
+        torch.cuda.synchronize()
+        if not (0.0 < k0.elapsed_time(k1) < 1e3):
+            raise RuntimeError("external events inside the graph returned no usable time")
+    except Exception as exc:  # noqa: BLE001
+        step_form = f"one CUDA graph per step; external events unavailable in capture ({exc!r}): kernel timed alone only"
+        gMarked = None
+    finally:
+        step.marks = {}
+        if args.streams != 2 and "base_fn" in locals():
+            dom.fn = base_fn
+    gFull = gMarked if gMarked is not None else capture(run_full)
+    # the split form: everything that precedes the dominant op, the op alone, everything after it
+    if args.streams == 2:
         pre, post = step.split_around(dom)
-        step.run_concurrent(pre); dom.fn(); step.run_concurrent(post)  # warm the side stream up
+        step.run_concurrent(pre); dom.fn(); step.run_concurrent(post)
         torch.cuda.synchronize()
         gA = capture(lambda: step.run_concurrent(pre))
         gB = capture(lambda: step.run_concurrent(post))
-        gFull = capture(lambda: step.run_concurrent(step.chains))
     else:
         before, after = step.ops[:dom_i], step.ops[dom_i + 1:]
         gA = capture(lambda: step.run(before)) if before else None
         gB = capture(lambda: step.run(after)) if after else None
-        gFull = capture(step.run)
-
-    def one_step(e0=None, e1=None):
-        if gA is not None:
-            gA.replay()
-        if e0 is not None:
-            e0.record()
-        dom.fn()
-        if e1 is not None:
-            e1.record()
-        if gB is not None:
-            gB.replay()
 
     sampler = ClockSampler(local)
     sampler.start()
     for _ in range(args.warmup):
         flush.zero_()
-        one_step()
+        gFull.replay()
     barrier()
     ops.reset_launch_count()
     t_wall0 = time.perf_counter()
-    marks = []
+    total_ms, inplace_ms = 0.0, 0.0
     for _ in range(args.steps):
         flush.zero_()
-        s0, e0, e1, s1 = ev(), ev(), ev(), ev()
+        s0, s1 = ev(), ev()
         s0.record()
-        one_step(e0, e1)
+        gFull.replay()
         s1.record()
-        marks.append((s0, e0, e1, s1))
+        s1.synchronize()  # between steps, outside the event pair: the in-graph events are re-recorded by the next replay
+        total_ms += s0.elapsed_time(s1)
+        if gMarked is not None:
+            inplace_ms += k0.elapsed_time(k1)
     barrier()
     t_wall1 = time.perf_counter()
+    # the dominant kernel alone inside the step (round 1's form of the step; comparable across rounds): nothing else
+    # runs between the two events, its launch is already queued behind graph A
+    alone_steps = max(5, min(args.steps, 50))
+    alone_ms = 0.0
+    for i in range(3 + alone_steps):
+        flush.zero_()
+        e0, e1 = ev(), ev()
+        if gA is not None:
+            gA.replay()
+        e0.record()
+        dom.fn()
+        e1.record()
+        if gB is not None:
+            gB.replay()
+        e1.synchronize()
+        if i >= 3:
+            alone_ms += e0.elapsed_time(e1)
+    barrier()
     eager_launches = ops.launch_count()  # launches issued through the ABI outside graph replays
-    total_ms = sum(s0.elapsed_time(s1) for s0, _, _, s1 in marks)
-    dom_ms = sum(e0.elapsed_time(e1) for _, e0, e1, _ in marks) / args.steps
+    dom_ms = alone_ms / alone_steps
+    inplace_us = inplace_ms / args.steps * 1e3 / max(1, dom.launches) if gMarked is not None else None
     clocks = sampler.summary(t_wall0, t_wall1)
 
     # ---- e2e: host inputs -> H2D -> step -> D2H results, all inside the timed region ---------------
@@ -417,7 +462,7 @@ def run_ours(args):
     # ---- the whole PWC-Lite training step around the path (cuDNN convs + loss + Adam are PyTorch) --------
     train_ms, train_info = 0.0, None
     if args.train_steps > 0:
-        del gA, gB, gFull
+        del gA, gB, gFull, gMarked
         train_ms, train_info = time_train_step(args, local, world, barrier)
 
     from unsamflow_b200 import dist_util
@@ -436,13 +481,18 @@ def run_ours(args):
             "config": workload_config(args, extra={
                 "l2": "256 MB L2 flush between timed steps (outside the per-step CUDA-event pair); "
                       "step working set ~1 GB > 126 MB L2",
-                "step": "CUDA graph A + eager dominant op between events + CUDA graph B",
+                "step": step_form,
                 "streams": args.streams, "batch_directions": args.batch_directions}),
             "hot_path_gbs": world * step.bytes_per_step * args.steps / (total_ms / 1e3) / 1e9,
             "hot_path_tflops": world * step.flops_per_step * args.steps / (total_ms / 1e3) / 1e12,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(dom), "kernel": dom.name, "kind": dom.kind, "shape": list(dom.shape),
                          "launches_per_op": launches, "alg_bytes_per_launch": alg, "us_per_launch": dom_us,
+                         "us_per_launch_in_place": inplace_us,
+                         "timing": f"us_per_launch: kernel alone between two CUDA events inside the step (graph A -> kernel -> "
+                                   f"graph B, {alone_steps} steps with the same L2 flush, run right after the timed steps); "
+                                   "us_per_launch_in_place: external events around the kernel inside every timed step's "
+                                   "graph, the other direction's stream running beside it",
                          "peak_source": peak_src,
                          "fp32_tflops": (dom.flops / launches) / dom_us / 1e6 if dom.flops else None,
                          "fp32_peak_tflops": FP32_PEAK_TFLOPS},
@@ -452,8 +502,8 @@ def run_ours(args):
                     "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps,
                     "pipeline": "double-buffered: H2D of step i+1 and D2H of step i-1 overlap the kernels of step i"},
             "gpu_launches": step.launches_per_step * args.steps,
-            "gpu_launches_note": f"{step.launches_per_step} usf kernels per step ({eager_launches} issued eagerly "
-                                 "through the C ABI in the timed region, the rest replayed from CUDA graphs)",
+            "gpu_launches_note": f"{step.launches_per_step} usf kernels per step, replayed from one CUDA graph in the timed "
+                                 f"region ({eager_launches} more issued eagerly through the C ABI by the kernel-alone loop)",
             "clocks": clocks,
         }
         if train_info is not None:

@@ -225,10 +225,16 @@ class HotPathStep:
         ("lwarp_*": 4 photometric scales, independent of each other, losses/flow_loss.py:120-131) fan out
         over `lanes` (one stream per scale) and join back."""
         cur = torch.cuda.current_stream()
+        marks = getattr(self, "marks", {})  # {op name: (event before, event after)} recorded on the op's stream
         i = 0
         while i < len(chain):
             if not chain[i].name.startswith("lwarp") or not lanes:
+                ev = marks.get(chain[i].name)
+                if ev is not None:
+                    ev[0].record(cur)
                 chain[i].fn()
+                if ev is not None:
+                    ev[1].record(cur)
                 i += 1
                 continue
             j = i
