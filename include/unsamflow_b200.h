@@ -19,6 +19,8 @@
  *   usf_occ_bidirection   utils/warp_utils.py:109-117 get_occu_mask_bidirection
  *                  (flow_warp(flow21, flow12, pad="zeros") + the forward-backward
  *                  consistency test), one kernel.
+ *   usf_segpool_fwd / _bwd  models/pwclite.py:317-340: the segment max-pooling of the mask-feature branch
+ *                  (one_hot x feature -> amax -> un-pool) of the "+mf" configs, and its gradient.
  *   usf_occ_backward      utils/warp_utils.py:26-94,120-126 get_occu_mask_backward
  *                  (get_corresponding_map's 4-tap forward splat + clamp + compare);
  *                  the mask losses/flow_loss.py:99-113 uses with occ_from_back.
@@ -165,6 +167,28 @@ size_t usf_occ_backward_workspace_bytes(int B, int H, int W);
  */
 int usf_occ_backward(const float *flow21, float *occ, float *range_map, int B, int H, int W, float th,
                      void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * Mask-feature pooling of the "+mf" configurations (models/pwclite.py:317-340, both images):
+ *   out[b,c,p] = max over the pixels q of p's segment of feat[b,c,q], clamped at 0 from below unless the segment
+ *   covers the whole image (the reference's amax runs over one_hot(seg) * feat, where the pixels outside a segment
+ *   contribute zeros) -- what `(one_hot * amax(one_hot * feat))).sum(-1)` computes, without its [B,C,h,w,N]
+ *   temporaries.
+ * feat, out: [B,C,H,W] (dtype).  seg: [B,H,W] int32 segment ids in [0, num_segments) (ids outside that range belong
+ * to no segment: out = 0, no gradient).  argmax: [B,C,num_segments] int32 or NULL (inference): the pixel index that
+ * attains each maximum (smallest index on ties), -1 where the clamp at 0 won; usf_segpool_bwd needs it.
+ * num_segments <= usf_segpool_max_segments().  Bit-reproducible (max is order independent).
+ */
+int usf_segpool_max_segments(void);
+int usf_segpool_fwd(const void *feat, const int *seg, void *out, int *argmax, int B, int C, int H, int W,
+                    int num_segments, int dtype, void *stream);
+/*
+ * Gradient of the pooling: gfeat[b,c,p] = sum of gout[b,c,.] over p's segment if p == argmax[b,c,seg[p]], else 0.
+ * The segment sums are formed in a fixed order (no float atomics): bit-reproducible.  Where several pixels tie for
+ * a maximum torch.amax splits the gradient evenly; here the first pixel takes it (measure zero for real features).
+ */
+int usf_segpool_bwd(const void *gout, const int *seg, const int *argmax, void *gfeat, int B, int C, int H, int W,
+                    int num_segments, int dtype, void *stream);
 
 #ifdef __cplusplus
 }

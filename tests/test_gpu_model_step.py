@@ -191,8 +191,8 @@ def _mf_step_main():
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.benchmark = False
 
-    def flows_with(corr_cls, warp):
-        pw.Correlation, pw.flow_warp = corr_cls, warp
+    def flows_with(corr_cls, warp, pool):
+        pw.Correlation, pw.flow_warp, pw.segment_max_pool = corr_cls, warp, pool
         torch.manual_seed(8)
         model = pw.PWCLite(add_mask_corr=True, aggregation_type="concat").cuda()
         model.init_weights()
@@ -207,8 +207,8 @@ def _mf_step_main():
         assert all(torch.isfinite(p.grad).all() for p in model.parameters())
         return [f.detach() for f in out["flows_12"] + out["flows_21"]]
 
-    port = flows_with(PortCorrelation, torch_port.flow_warp)
-    mine = flows_with(usf.Correlation, partial(usf.flow_warp, coord_reciprocal=True))
+    port = flows_with(PortCorrelation, torch_port.flow_warp, lambda f, s, n=None: pw.segment_max_pool_torch(f, s))
+    mine = flows_with(usf.Correlation, partial(usf.flow_warp, coord_reciprocal=True), usf.segment_max_pool)
     worst = max(rel(a, b) for a, b in zip(mine, port))
     assert worst <= 1e-3, worst
     print("mf step ok, worst flow rel-L2", worst)

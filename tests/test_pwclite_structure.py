@@ -26,6 +26,7 @@ class _PortCorr(torch.nn.Module):
 def cpu_ops(monkeypatch):
     monkeypatch.setattr(pwclite_mod, "Correlation", _PortCorr)
     monkeypatch.setattr(pwclite_mod, "flow_warp", torch_port.flow_warp)
+    monkeypatch.setattr(pwclite_mod, "segment_max_pool", lambda feat, seg, n=None: pwclite_mod.segment_max_pool_torch(feat, seg))
     monkeypatch.setattr(flow_loss_mod, "flow_warp", torch_port.flow_warp)
     monkeypatch.setattr(flow_loss_mod, "get_occu_mask_backward", torch_port.occ_mask_backward)
     monkeypatch.setattr(flow_loss_mod, "get_occu_mask_bidirection", torch_port.occ_mask_bidirection)
@@ -167,7 +168,7 @@ def test_segment_max_pool_equals_the_one_hot_formulation(case):
         seg = seg * 3                     # ids 0,3,6,...: empty classes in between
     a = feat.clone().requires_grad_(True)
     b = feat.clone().requires_grad_(True)
-    mine, ref = pwclite_mod.segment_max_pool(a, seg), _onehot_pool(b, seg)
+    mine, ref = pwclite_mod.segment_max_pool_torch(a, seg), _onehot_pool(b, seg)
     assert torch.equal(mine, ref)
     g = torch.randn(mine.shape, generator=gen)
     mine.backward(g)

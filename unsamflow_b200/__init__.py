@@ -9,8 +9,9 @@ include/unsamflow_b200.h; there is no CPU or PyTorch fallback.
 """
 from .correlation import Correlation, CorrelationFunction  # noqa: F401
 from .occlusion import get_occu_mask_backward, get_occu_mask_bidirection  # noqa: F401
+from .segpool import segment_max_pool  # noqa: F401
 from .warp import FlowWarpFunction, flow_warp  # noqa: F401
 
 __all__ = ["Correlation", "CorrelationFunction", "FlowWarpFunction", "flow_warp",
-           "get_occu_mask_backward", "get_occu_mask_bidirection"]
+           "get_occu_mask_backward", "get_occu_mask_bidirection", "segment_max_pool"]
 __version__ = "0.1.0"

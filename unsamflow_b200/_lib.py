@@ -23,7 +23,8 @@ SYMBOLS = (
     "usf_abi_version", "usf_status_string", "usf_last_cuda_error", "usf_launch_count",
     "usf_reset_launch_count", "usf_corr_fwd", "usf_corr_bwd", "usf_warp_fwd",
     "usf_warp_bwd_workspace_bytes", "usf_warp_bwd_workspace_clean_bytes", "usf_warp_bwd", "usf_occ_bidirection",
-    "usf_occ_backward_workspace_bytes", "usf_occ_backward",
+    "usf_occ_backward_workspace_bytes", "usf_occ_backward", "usf_segpool_max_segments", "usf_segpool_fwd",
+    "usf_segpool_bwd",
 )
 
 _lib = None
@@ -68,6 +69,11 @@ def load():
     L.usf_occ_backward_workspace_bytes.argtypes = [i, i, i]
     L.usf_occ_backward.restype = i
     L.usf_occ_backward.argtypes = [vp, vp, vp, i, i, i, f, vp, sz, vp]
+    L.usf_segpool_max_segments.restype = i
+    L.usf_segpool_fwd.restype = i
+    L.usf_segpool_fwd.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, vp]
+    L.usf_segpool_bwd.restype = i
+    L.usf_segpool_bwd.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, vp]
     if L.usf_abi_version() != ABI_VERSION:
         raise ImportError(f"{LIB_PATH}: ABI {L.usf_abi_version()} != expected {ABI_VERSION}; rebuild")
     _lib = L

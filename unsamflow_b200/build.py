@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB_DIR = os.path.join(PKG, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libunsamflow_b200.so")
-SOURCES = ["api.cu", "corr_fwd.cu", "corr_bwd.cu", "corr_direct.cu", "corr_small.cu", "corr_fwd_bf16.cu", "corr_bwd_bf16.cu", "warp.cu", "occ.cu"]
+SOURCES = ["api.cu", "corr_fwd.cu", "corr_bwd.cu", "corr_direct.cu", "corr_small.cu", "corr_fwd_bf16.cu", "corr_bwd_bf16.cu", "warp.cu", "occ.cu", "segpool.cu"]
 HEADERS = ["common.cuh", "tma.cuh", "warp_coord.cuh", os.path.join("..", "..", "include", "unsamflow_b200.h")]
 
 NVCC_FLAGS = [

@@ -34,6 +34,9 @@ int corr_bwd_small_bf16(const void *, const void *, const void *, void *, void *
 int occ_bidirection(const float *, const float *, float *, int, int, int, float, float, unsigned, cudaStream_t);
 size_t occ_backward_workspace_bytes(int B, int H, int W);
 int occ_backward(const float *, float *, float *, int, int, int, float, void *, cudaStream_t);
+int segpool_max_segments();
+int segpool_fwd(const void *, const int *, void *, int *, int, int, int, int, int, cudaStream_t);
+int segpool_bwd(const void *, const int *, const int *, void *, int, int, int, int, int, cudaStream_t);
 bool corr_small_applies(int H, int W);  // whole image <= 256 pixels: corr_small.cu
 
 long kDirectMaxPixels = [] {
@@ -248,4 +251,26 @@ int usf_occ_backward(const float *flow21, float *occ, float *range_map, int B, i
     return occ_backward(flow21, occ, range_map, B, H, W, th, workspace, (cudaStream_t)stream);
 }
 
-}  // extern "C"
+int usf_segpool_max_segments(void) { return segpool_max_segments(); }
+
+int usf_segpool_fwd(const void *feat, const int *seg, void *out, int *argmax, int B, int C, int H, int W,
+                    int num_segments, int dtype, void *stream) {
+    if (!feat || !seg || !out) return USF_ERR_BAD_ARG;
+    if (dtype != USF_F32 && dtype != USF_BF16) return USF_ERR_BAD_ARG;
+    if (int st = check_dims(B, C, H, W, 1)) return st;
+    if (num_segments < 1 || num_segments > segpool_max_segments()) return USF_ERR_BAD_SHAPE;
+    if ((long long)B * C * num_segments > 2147483647LL) return USF_ERR_BAD_SHAPE;
+    return segpool_fwd(feat, seg, out, argmax, B, C, H * W, num_segments, dtype, (cudaStream_t)stream);
+}
+
+int usf_segpool_bwd(const void *gout, const int *seg, const int *argmax, void *gfeat, int B, int C, int H, int W,
+                    int num_segments, int dtype, void *stream) {
+    if (!gout || !seg || !argmax || !gfeat) return USF_ERR_BAD_ARG;
+    if (dtype != USF_F32 && dtype != USF_BF16) return USF_ERR_BAD_ARG;
+    if (int st = check_dims(B, C, H, W, 1)) return st;
+    if (num_segments < 1 || num_segments > segpool_max_segments()) return USF_ERR_BAD_SHAPE;
+    if ((long long)B * C * num_segments > 2147483647LL) return USF_ERR_BAD_SHAPE;
+    return segpool_bwd(gout, seg, argmax, gfeat, B, C, H * W, num_segments, dtype, (cudaStream_t)stream);
+}
+
+}

@@ -12,9 +12,10 @@ exactly as in the reference; the call sites are
     x_mask_feat2_warp = flow_warp(x_mask_feat2, flow)             models/pwclite.py:355   (add_mask_corr)
     out_mask_corr = self.corr(x_mask_feat1, x_mask_feat2_warp)    models/pwclite.py:356   (add_mask_corr)
 
-The segment pooling in front of the second pair (models/pwclite.py:317-340) is restated as a segmented max +
-gather (`segment_max_pool`) instead of the reference's one-hot product, whose [B,32,h,w,N] temporaries reach
-gigabytes at B=8; same values and gradients.
+The segment pooling in front of the second pair (models/pwclite.py:317-340) runs as a segmented max + gather in
+hand-written kernels (unsamflow_b200/segpool.py, csrc/segpool.cu) instead of the reference's one-hot product, whose
+[B,32,h,w,N] temporaries reach gigabytes at B=8; same values and gradients
+(`segment_max_pool_torch` is the PyTorch formulation the tests check it against).
 
 Layer shapes follow the reference so that the parameter count (2,513,412) and a state-dict loaded
 position-by-position from the reference model agree (tests/test_pwclite_structure.py).
@@ -26,6 +27,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .correlation import Correlation
+from .segpool import segment_max_pool
 from .warp import flow_warp
 
 PYRAMID_CHANNELS = (3, 16, 32, 64, 96, 128, 192)  # models/pwclite.py:183
@@ -110,8 +112,11 @@ class ConvexUpsampler(nn.Module):
         return up.reshape(n, 2, s * h, s * w)
 
 
-def segment_max_pool(feat, seg):
-    """feat [B,C,h,w], seg [B,1,h,w] integer ids -> every pixel receives the maximum of `feat` over its segment.
+def segment_max_pool_torch(feat, seg):
+    """PyTorch formulation of the pooling, kept as the checker of the CUDA kernel (tests) and for CPU structure
+    tests; the model calls unsamflow_b200.segpool.segment_max_pool (csrc/segpool.cu).
+
+    feat [B,C,h,w], seg [B,1,h,w] integer ids -> every pixel receives the maximum of `feat` over its segment.
 
     Restates models/pwclite.py:319-328: `amax(one_hot(seg) * feat[..., None], dim=(2, 3))` followed by the
     one-hot weighted sum.  In that product the pixels outside a segment contribute zeros, so the pooled value is
@@ -129,8 +134,11 @@ def segment_max_pool(feat, seg):
 
 
 class PWCLite(nn.Module):
-    def __init__(self, batch_directions=False, add_mask_corr=False, aggregation_type="concat"):
+    def __init__(self, batch_directions=False, add_mask_corr=False, aggregation_type="concat", num_segments=None):
+        """num_segments: one-hot classes of the segment maps (max id + 1); None reads it from the map on every call
+        (a device->host sync, like the reference's F.one_hot); e.g. 256 for uint8 SAM id maps keeps the step sync-free."""
         super().__init__()
+        self.num_segments = num_segments
         self.batch_directions = batch_directions
         self.add_mask_corr = add_mask_corr
         self.aggregation_type = aggregation_type
@@ -152,7 +160,7 @@ class PWCLite(nn.Module):
     def mask_features(self, level, x, seg):
         """models/pwclite.py:317-351 for one image: 1x1 conv, pooling over the SAM segments, aggregation."""
         proj = self.conv_1x1_mask[level](x)
-        pooled = segment_max_pool(proj, F.interpolate(seg, x.shape[-2:], mode="nearest"))
+        pooled = segment_max_pool(proj, F.interpolate(seg, x.shape[-2:], mode="nearest"), self.num_segments)
         if self.aggregation_type == "residual":
             return proj + self.mask_aggregation(pooled)
         return self.mask_aggregation(torch.cat([proj, pooled], 1))
