@@ -105,6 +105,17 @@ int usf_corr_fwd(const void *x1, const void *x2, void *out, int B, int C, int H,
                  int max_disp, int dtype, unsigned flags, float leaky_slope, void *stream);
 
 /*
+ * The same cost volume written into a channel slice of a wider tensor: `out` points at the first of the 81
+ * channels inside image 0 and consecutive images are `out_batch_stride` ELEMENTS apart (>= 81*H*W).  With
+ * USF_FLAG_LEAKY_RELU this is models/pwclite.py:307-308 + the cost-volume part of the torch.cat at :364-366 in one
+ * kernel: the estimator's input buffer [B, 81 + 32 + 2, H, W] receives LeakyReLU(corr) directly.
+ * Vectorised stores need out_batch_stride % 4 == 0 (bf16: % 8) next to the usual 16-byte alignment of `out`; other
+ * strides take the scalar-store kernels.
+ */
+int usf_corr_fwd_into(const void *x1, const void *x2, void *out, long long out_batch_stride, int B, int C, int H,
+                      int W, int max_disp, int dtype, unsigned flags, float leaky_slope, void *stream);
+
+/*
  * Gradients of the cost volume.  gout: [B,81,H,W].  gx1 / gx2: [B,C,H,W], either
  * may be NULL (not needed).  Both are computed as gathers: no atomics, outputs
  * fully overwritten, bit-identical from run to run.  (Images of <= 256 pixels are

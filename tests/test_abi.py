@@ -27,7 +27,7 @@ def declared_symbols():
 def test_header_symbols_are_exported(lib):
     from unsamflow_b200 import _lib
     names = declared_symbols()
-    assert len(names) == 17
+    assert len(names) == 18
     assert sorted(_lib.SYMBOLS) == names
     for n in names:
         assert getattr(lib, n) is not None

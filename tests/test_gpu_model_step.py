@@ -229,3 +229,37 @@ def test_mask_feature_config_step_on_the_usf_ops():
             "t._mf_step_main()" % (os.path.dirname(here), here))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_fused_cost_concat_model_equals_the_unfused_one(exact_math):
+    """PWCLite(fuse_cost_concat=True): the correlation kernels apply LeakyReLU and write into the estimator's input
+    buffer.  Same weights, same inputs: forward bit-identical to corr -> LeakyReLU -> cat,
+    parameter gradients equal up to summation order; with and without the mask-feature pair."""
+    import unsamflow_b200.pwclite as pw
+    for mf in (False, True):
+        torch.manual_seed(11)
+        plain = pw.PWCLite(add_mask_corr=mf, num_segments=40).cuda()
+        plain.init_weights()
+        fused = pw.PWCLite(add_mask_corr=mf, num_segments=40, fuse_cost_concat=True).cuda()
+        fused.load_state_dict(plain.state_dict())
+        gen = torch.Generator().manual_seed(12)
+        img1, img2 = torch.rand(2, 3, 128, 256, generator=gen).cuda(), torch.rand(2, 3, 128, 256, generator=gen).cuda()
+        segs = ()
+        if mf:
+            coarse = torch.randint(0, 40, (2, 1, 8, 16), generator=gen).float()
+            s1 = torch.nn.functional.interpolate(coarse, (128, 256), mode="nearest").cuda()
+            segs = (s1, torch.roll(s1, 7, dims=-1))
+        outs = []
+        for model in (plain, fused):
+            out = model(img1, img2, *segs, with_bk=True)
+            sum(f.abs().mean() for f in out["flows_12"] + out["flows_21"]).backward()
+            outs.append(out)
+        for k in ("flows_12", "flows_21"):
+            for a, b in zip(outs[0][k], outs[1][k]):
+                assert torch.equal(a, b), (mf, k)
+        worst = 0.0
+        for (n, p), (_, q) in zip(plain.named_parameters(), fused.named_parameters()):
+            assert (p.grad is None) == (q.grad is None), n
+            if p.grad is not None:
+                worst = max(worst, rel(q.grad, p.grad))
+        assert worst <= 1e-5, (mf, worst)

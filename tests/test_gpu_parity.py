@@ -191,6 +191,60 @@ WARP_SHAPES = [
 ]
 
 
+@pytest.mark.parametrize("shape", [(2, 32, 64, 208), (2, 64, 32, 104), (2, 96, 16, 52), (2, 128, 8, 26), (2, 192, 4, 13),
+                                   (1, 17, 9, 31), (2, 20, 40, 36), (3, 8, 70, 30)], ids=lambda s: "x".join(map(str, s)))
+def test_corr_fwd_into_a_channel_slice(usf, shape):
+    """usf_corr_fwd_into: the cost volume lands in channels [k, k+81) of a wider tensor (the estimator's concat buffer,
+    models/pwclite.py:364-366), bit-identical to the dense result, nothing outside the slice touched -- every kernel
+    family (TMA tiles, split-channel, whole-image, direct) and both epilogues."""
+    ops = usf.ops_mod
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(40 + C)
+    x1, x2 = torch.randn(shape, generator=g).cuda(), torch.randn(shape, generator=g).cuda()
+    for slope in (None, 0.1):
+        dense = ops.corr_fwd(x1, x2, leaky_slope=slope)
+        for ctot, k in ((81 + 34, 0), (81 + 81 + 34, 81), (90, 5)):   # (90, 5): slice start not 16-byte aligned for odd H*W
+            buf = torch.full((B, ctot, H, W), 7.0, device="cuda")
+            ops.corr_fwd(x1, x2, leaky_slope=slope, out=buf[:, k:k + 81])
+            assert torch.equal(buf[:, k:k + 81], dense), (slope, ctot, k)
+            rest = torch.cat([buf[:, :k], buf[:, k + 81:]], 1)
+            assert bool((rest == 7.0).all()), "wrote outside the slice"
+    with pytest.raises(ValueError):
+        ops.corr_fwd(x1, x2, out=torch.empty(B, 81, H, 2 * W, device="cuda")[..., ::2])
+    hb = x1.bfloat16(), x2.bfloat16()
+    dense = ops.corr_fwd(*hb, leaky_slope=0.1)
+    buf = torch.zeros(B, 115, H, W, device="cuda", dtype=torch.bfloat16)
+    ops.corr_fwd(*hb, leaky_slope=0.1, out=buf[:, :81])
+    assert torch.equal(buf[:, :81], dense) and float(buf[:, 81:].abs().max()) == 0.0
+
+
+def test_cost_concat_equals_corr_leaky_cat(usf):
+    """correlation.cost_concat (kernel-side LeakyReLU + write into the concat buffer) against the reference's
+    sequence corr -> LeakyReLU(inplace) -> torch.cat, values and gradients, one and two feature pairs."""
+    from unsamflow_b200.correlation import cost_concat
+    corr = usf.Correlation(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1, corr_multiply=1)
+    g = torch.Generator().manual_seed(50)
+    B, C, H, W = 2, 32, 32, 104
+    base = [torch.randn(B, C, H, W, generator=g).cuda() for _ in range(4)] + \
+           [torch.randn(B, 32, H, W, generator=g).cuda(), torch.randn(B, 2, H, W, generator=g).cuda()]
+    for n_pairs in (1, 2):
+        a = [t.clone().requires_grad_(True) for t in base]
+        b = [t.clone().requires_grad_(True) for t in base]
+        pa = [(a[0], a[1]), (a[2], a[3])][:n_pairs]
+        pb = [(b[0], b[1]), (b[2], b[3])][:n_pairs]
+        fused = cost_concat(pa, [a[4], a[5]], 0.1)
+        ref = torch.cat([torch.nn.functional.leaky_relu(corr(p, q), 0.1) for p, q in pb] + [b[4], b[5]], 1)
+        assert torch.equal(fused, ref)
+        go = torch.randn(ref.shape, generator=g).cuda()
+        fused.backward(go)
+        ref.backward(go)
+        for i, (u, v) in enumerate(zip(a, b)):
+            if i >= 2 * n_pairs and i < 4:
+                assert u.grad is None and v.grad is None
+                continue
+            assert torch.allclose(u.grad, v.grad, rtol=1e-6, atol=1e-7), i
+
+
 @pytest.mark.parametrize("pad", ["border", "zeros"])
 @pytest.mark.parametrize("kind", ["gauss", "wild", "integer", "subpixel_edges"])
 @pytest.mark.parametrize("shape", WARP_SHAPES, ids=lambda s: "x".join(map(str, s)))

@@ -21,7 +21,7 @@ FLAG_WORKSPACE_CLEAN = 8
 # every symbol include/unsamflow_b200.h declares (tests/test_abi.py checks header <-> library <-> this list)
 SYMBOLS = (
     "usf_abi_version", "usf_status_string", "usf_last_cuda_error", "usf_launch_count",
-    "usf_reset_launch_count", "usf_corr_fwd", "usf_corr_bwd", "usf_warp_fwd",
+    "usf_reset_launch_count", "usf_corr_fwd", "usf_corr_fwd_into", "usf_corr_bwd", "usf_warp_fwd",
     "usf_warp_bwd_workspace_bytes", "usf_warp_bwd_workspace_clean_bytes", "usf_warp_bwd", "usf_occ_bidirection",
     "usf_occ_backward_workspace_bytes", "usf_occ_backward", "usf_segpool_max_segments", "usf_segpool_fwd",
     "usf_segpool_bwd",
@@ -53,6 +53,8 @@ def load():
     L.usf_reset_launch_count.restype = None
     L.usf_corr_fwd.restype = i
     L.usf_corr_fwd.argtypes = [vp, vp, vp, i, i, i, i, i, i, u, f, vp]
+    L.usf_corr_fwd_into.restype = i
+    L.usf_corr_fwd_into.argtypes = [vp, vp, vp, ctypes.c_longlong, i, i, i, i, i, i, u, f, vp]
     L.usf_corr_bwd.restype = i
     L.usf_corr_bwd.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, i, i, u, vp]
     L.usf_warp_fwd.restype = i

@@ -44,6 +44,9 @@ long kDirectMaxPixels = [] {
     return e ? atol(e) : 4096L;
 }();
 
+static thread_local size_t tl_out_bstride = 0;  // 0: dense [B,81,H,W]
+size_t corr_out_bstride(int H, int W) { return tl_out_bstride ? tl_out_bstride : (size_t)kK * H * W; }
+
 int sm_count() {
     static std::mutex mu;
     static int cache[64] = {0};
@@ -155,6 +158,16 @@ int usf_corr_fwd(const void *x1, const void *x2, void *out, int B, int C, int H,
         return corr_fwd_bf16(x1, x2, out, B, C, H, W, flags, leaky_slope, (cudaStream_t)stream);
     }
     return USF_ERR_BAD_ARG;
+}
+
+int usf_corr_fwd_into(const void *x1, const void *x2, void *out, long long out_batch_stride, int B, int C, int H,
+                      int W, int max_disp, int dtype, unsigned flags, float leaky_slope, void *stream) {
+    if (out_batch_stride < (long long)kK * H * W) return USF_ERR_BAD_SHAPE;
+    if ((long long)B * out_batch_stride > 2147483647LL) return USF_ERR_BAD_SHAPE;
+    tl_out_bstride = (size_t)out_batch_stride;
+    const int st = usf_corr_fwd(x1, x2, out, B, C, H, W, max_disp, dtype, flags, leaky_slope, stream);
+    tl_out_bstride = 0;
+    return st;
 }
 
 int usf_corr_bwd(const void *x1, const void *x2, const void *gout, void *gx1, void *gx2, int B, int C,

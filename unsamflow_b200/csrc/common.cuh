@@ -24,6 +24,11 @@ void note_cuda_error(cudaError_t e);
 // cudaFuncSetAttribute is per device, so a process that drives several GPUs is handled too.
 cudaError_t ensure_smem(const void *kernel, int smem_bytes);
 
+// Output batch stride of the correlation forward, in elements: 81*H*W for a dense [B,81,H,W] cost volume, larger when
+// the caller points `out` at a channel slice of a wider tensor (usf_corr_fwd_into: the estimator's concat buffer,
+// models/pwclite.py:364-366).  api.cu parks the requested value in a thread-local for the duration of the call.
+size_t corr_out_bstride(int H, int W);
+
 // ---- launches ---------------------------------------------------------------
 // Every hot-path kernel is launched with programmatic stream serialization and starts with griddepcontrol.wait:
 // the semantics are those of plain stream order (the wait returns when the preceding kernel of the stream has

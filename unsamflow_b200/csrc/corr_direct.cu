@@ -21,7 +21,7 @@ constexpr int kFwdOutputs = 32, kFwdSlices = 8, kFwdThreads = kFwdOutputs * kFwd
 template <bool LEAKY, typename T>
 __global__ void __launch_bounds__(kFwdThreads)
 corr_fwd_direct(const T *__restrict__ x1, const T *__restrict__ x2, T *__restrict__ out, int total,
-                int C, int H, int W, float rc, float slope) {
+                int C, int H, int W, float rc, float slope, size_t obs) {
     __shared__ float red[kFwdSlices][kFwdOutputs];
     const int lane = threadIdx.x & 31, cs = threadIdx.x >> 5;  // one warp == one channel slice
     const int idx = blockIdx.x * kFwdOutputs + lane;
@@ -54,7 +54,8 @@ corr_fwd_direct(const T *__restrict__ x1, const T *__restrict__ x2, T *__restric
     for (int s = 1; s < kFwdSlices; ++s) sum += red[s][lane];
     float v = sum * rc;
     if (LEAKY) v = v < 0.f ? v * slope : v;
-    stf(out + idx, v);
+    const int ob = idx / (HW * kK);  // image index: the cost volume may be a channel slice of a wider tensor
+    stf(out + (size_t)ob * obs + (idx - ob * HW * kK), v);
 }
 
 // ---- backward: one thread = 4 channels of one pixel x one third of the displacement rows ----------
@@ -134,9 +135,9 @@ static int fwd_direct(const T *x1, const T *x2, T *out, int B, int C, int H, int
     const int blocks = (total + kFwdOutputs - 1) / kFwdOutputs;
     const float rc = 1.0f / (float)C;
     if (flags & USF_FLAG_LEAKY_RELU)
-        corr_fwd_direct<true, T><<<blocks, kFwdThreads, 0, stream>>>(x1, x2, out, total, C, H, W, rc, slope);
+        corr_fwd_direct<true, T><<<blocks, kFwdThreads, 0, stream>>>(x1, x2, out, total, C, H, W, rc, slope, corr_out_bstride(H, W));
     else
-        corr_fwd_direct<false, T><<<blocks, kFwdThreads, 0, stream>>>(x1, x2, out, total, C, H, W, rc, slope);
+        corr_fwd_direct<false, T><<<blocks, kFwdThreads, 0, stream>>>(x1, x2, out, total, C, H, W, rc, slope, corr_out_bstride(H, W));
     return note_launch(cudaGetLastError());
 }
 

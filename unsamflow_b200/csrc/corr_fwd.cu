@@ -132,7 +132,7 @@ constexpr int A_SMEM = NST * A_STAGE * 4;                // 95232 B
 template <bool VEC>
 __global__ void __maxnreg__(112)
 corr_fwd_tile9(const float *__restrict__ x1, const float *__restrict__ x2, float *__restrict__ out, int C,
-               int H, int W, float rc, int leaky, float slope) {
+               int H, int W, float rc, int leaky, float slope, size_t obs) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r = lane >> 2, q = lane & 3;
@@ -171,7 +171,7 @@ corr_fwd_tile9(const float *__restrict__ x1, const float *__restrict__ x2, float
 
     const int gy = y0 + r, gx = x0 + 8 * q;
     if (gy >= H) return;
-    float *o = out + (((size_t)b * kK + warp * kD) * H + gy) * W + gx;
+    float *o = out + (size_t)b * obs + (((size_t)warp * kD) * H + gy) * W + gx;
     const size_t kstride = (size_t)H * W;
 #pragma unroll
     for (int dx = 0; dx < kD; ++dx, o += kstride) {
@@ -202,7 +202,7 @@ constexpr int B_SMEM = (B_RED > NST * B_STAGE ? B_RED : NST * B_STAGE) * 4;
 template <bool VEC>
 __global__ void __launch_bounds__(B_THREADS, 2)
 corr_fwd_splitc(const float *__restrict__ x1, const float *__restrict__ x2, float *__restrict__ out, int C,
-                int H, int W, float rc, int leaky, float slope) {
+                int H, int W, float rc, int leaky, float slope, size_t obs) {
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int r = lane >> 2, q = lane & 3;
@@ -250,7 +250,7 @@ corr_fwd_splitc(const float *__restrict__ x1, const float *__restrict__ x2, floa
     }
     __syncthreads();
     // 9*8*32 = 2304 outputs, 9 per thread, x fastest -> coalesced 128-byte rows
-    float *ob = out + ((size_t)b * kK + dyi * kD) * H * W;
+    float *ob = out + (size_t)b * obs + ((size_t)dyi * kD) * H * W;
 #pragma unroll
     for (int m = 0; m < kD; ++m) {
         const int e = tid + m * B_THREADS;
@@ -298,11 +298,11 @@ template <bool PIPE> struct T9Cfg {
 // lanes (r,q) and (r^1,q) swap halves, then one instruction writes both 16-byte halves of a sector.
 template <bool LEAKY>
 __device__ __forceinline__ void store_tile(float (&acc)[kD][8], float *__restrict__ out, int b, int dyi, int y0,
-                                           int x0, int r, int q, int H, int W, float rc, float slope) {
+                                           int x0, int r, int q, int H, int W, float rc, float slope, size_t obs) {
     const bool odd = r & 1;
     const int row0 = y0 + (r & ~1), gx = x0 + 8 * q + (odd ? 4 : 0);
     const size_t kstride = (size_t)H * W;
-    float *o = out + (((size_t)b * kK + dyi * kD) * H + row0) * W + gx;
+    float *o = out + (size_t)b * obs + (((size_t)dyi * kD) * H + row0) * W + gx;
     const bool c_ok = gx < W, r0_ok = row0 < H, r1_ok = row0 + 1 < H;
 #pragma unroll
     for (int dx = 0; dx < kD; ++dx, o += kstride) {
@@ -327,7 +327,7 @@ template <bool LEAKY, bool PIPE>
 __global__ void __launch_bounds__(TA_THREADS, T9Cfg<PIPE>::kMinBlocks)
 corr_fwd_tile9_tma(const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
                    float *__restrict__ out, int C, int H, int W, int tiles_x, int tiles_y, int ntiles, float rc,
-                   float slope) {
+                   float slope, size_t obs) {
     pdl_wait();
     constexpr int NS = T9Cfg<PIPE>::kStages;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -398,7 +398,7 @@ corr_fwd_tile9_tma(const __grid_constant__ CUtensorMap m1, const __grid_constant
             release_stage_reads();
             if (lane == 0) mbar_arrive(&empty_bar[s]);
         }
-        store_tile<LEAKY>(acc, out, b, warp, ty * TH, tx * TW, r, q, H, W, rc, slope);
+        store_tile<LEAKY>(acc, out, b, warp, ty * TH, tx * TW, r, q, H, W, rc, slope, obs);
     }
 }
 
@@ -412,7 +412,7 @@ constexpr int TB_SMEM = (B_RED * 4 > TB_NST * TB_STAGE_BYTES) ? B_RED * 4 : TB_N
 template <bool LEAKY>
 __global__ void __launch_bounds__(TB_THREADS, 2)
 corr_fwd_splitc_tma(const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
-                    float *__restrict__ out, int C, int H, int W, float rc, float slope) {
+                    float *__restrict__ out, int C, int H, int W, float rc, float slope, size_t obs) {
     pdl_wait();
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[TB_NST], empty_bar[TB_NST];
@@ -472,7 +472,7 @@ corr_fwd_splitc_tma(const __grid_constant__ CUtensorMap m1, const __grid_constan
         *reinterpret_cast<float4 *>(p + 4) = make_float4(acc[dx][4], acc[dx][5], acc[dx][6], acc[dx][7]);
     }
     asm volatile("bar.sync 1, %0;\n" ::"n"(32 * B_WARPS) : "memory");
-    float *ob = out + ((size_t)b * kK + dyi * kD) * H * W;
+    float *ob = out + (size_t)b * obs + ((size_t)dyi * kD) * H * W;
 #pragma unroll
     for (int m = 0; m < kD; ++m) {
         const int e = tid + m * (32 * B_WARPS);
@@ -490,10 +490,11 @@ template <bool LEAKY>
 cudaError_t launch_tma(bool splitc, const CUtensorMap &m1, const CUtensorMap &m2a, const CUtensorMap &m2b,
                        float *out, int B, int C, int H, int W, int tx, int ty, float rc, float slope,
                        cudaStream_t stream) {
+    const size_t obs = corr_out_bstride(H, W);
     if (splitc) {
         cudaError_t once = ensure_smem((const void *)corr_fwd_splitc_tma<LEAKY>, TB_SMEM);
         if (once != cudaSuccess) return once;
-        usf_launch(corr_fwd_splitc_tma<LEAKY>, dim3(dim3(tx, ty, B * kD)), dim3(TB_THREADS), TB_SMEM, stream, m1, m2b, out, C, H, W, rc, slope);
+        usf_launch(corr_fwd_splitc_tma<LEAKY>, dim3(dim3(tx, ty, B * kD)), dim3(TB_THREADS), TB_SMEM, stream, m1, m2b, out, C, H, W, rc, slope, obs);
     } else {
         const int ntiles = tx * ty * B;
         const int sms = sm_count();
@@ -502,13 +503,13 @@ cudaError_t launch_tma(bool splitc, const CUtensorMap &m1, const CUtensorMap &m2
             if (once != cudaSuccess) return once;
             const int grid = ntiles < sms ? ntiles : sms;
             usf_launch((corr_fwd_tile9_tma<LEAKY, true>), dim3(grid), dim3(TA_THREADS), T9Cfg<true>::kSmem, stream, 
-                m1, m2a, out, C, H, W, tx, ty, ntiles, rc, slope);
+                m1, m2a, out, C, H, W, tx, ty, ntiles, rc, slope, obs);
         } else {
             cudaError_t once = ensure_smem((const void *)corr_fwd_tile9_tma<LEAKY, false>, T9Cfg<false>::kSmem);
             if (once != cudaSuccess) return once;
             const int grid = ntiles < 2 * sms ? ntiles : 2 * sms;
             usf_launch((corr_fwd_tile9_tma<LEAKY, false>), dim3(grid), dim3(TA_THREADS), T9Cfg<false>::kSmem, stream, 
-                m1, m2a, out, C, H, W, tx, ty, ntiles, rc, slope);
+                m1, m2a, out, C, H, W, tx, ty, ntiles, rc, slope, obs);
         }
     }
     return cudaGetLastError();
@@ -524,7 +525,8 @@ int corr_fwd_f32(const float *x1, const float *x2, float *out, int B, int C, int
     // them to corr_small.cu): L1/L2 resident -> direct kernel (corr_direct.cu); widths TMA can address go to the
     // tiled kernels even when small
     if ((long)B * H * W <= kDirectMaxPixels && (W % 4) != 0) return corr_fwd_direct_f32(x1, x2, out, B, C, H, W, flags, slope, stream);
-    const bool vec = (W % 4 == 0) && (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) % 16 == 0);
+    const size_t obs = corr_out_bstride(H, W);
+    const bool vec = (W % 4 == 0) && (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) % 16 == 0) && obs % 4 == 0;
     const int tx = (W + TW - 1) / TW, ty = (H + TH - 1) / TH;
     const float rc = 1.0f / (float)C;
     const int leaky = (flags & USF_FLAG_LEAKY_RELU) ? 1 : 0;
@@ -548,19 +550,19 @@ int corr_fwd_f32(const float *x1, const float *x2, float *out, int B, int C, int
         dim3 grid(tx, ty, B * kD);
         if (vec) {
             if (cudaError_t once = ensure_smem((const void *)corr_fwd_splitc<true>, B_SMEM)) return note_launch(once);
-            corr_fwd_splitc<true><<<grid, B_THREADS, B_SMEM, stream>>>(x1, x2, out, C, H, W, rc, leaky, slope);
+            corr_fwd_splitc<true><<<grid, B_THREADS, B_SMEM, stream>>>(x1, x2, out, C, H, W, rc, leaky, slope, obs);
         } else {
             if (cudaError_t once = ensure_smem((const void *)corr_fwd_splitc<false>, B_SMEM)) return note_launch(once);
-            corr_fwd_splitc<false><<<grid, B_THREADS, B_SMEM, stream>>>(x1, x2, out, C, H, W, rc, leaky, slope);
+            corr_fwd_splitc<false><<<grid, B_THREADS, B_SMEM, stream>>>(x1, x2, out, C, H, W, rc, leaky, slope, obs);
         }
     } else {
         dim3 grid(tx, ty, B);
         if (vec) {
             if (cudaError_t once = ensure_smem((const void *)corr_fwd_tile9<true>, A_SMEM)) return note_launch(once);
-            corr_fwd_tile9<true><<<grid, A_THREADS, A_SMEM, stream>>>(x1, x2, out, C, H, W, rc, leaky, slope);
+            corr_fwd_tile9<true><<<grid, A_THREADS, A_SMEM, stream>>>(x1, x2, out, C, H, W, rc, leaky, slope, obs);
         } else {
             if (cudaError_t once = ensure_smem((const void *)corr_fwd_tile9<false>, A_SMEM)) return note_launch(once);
-            corr_fwd_tile9<false><<<grid, A_THREADS, A_SMEM, stream>>>(x1, x2, out, C, H, W, rc, leaky, slope);
+            corr_fwd_tile9<false><<<grid, A_THREADS, A_SMEM, stream>>>(x1, x2, out, C, H, W, rc, leaky, slope, obs);
         }
     }
     e = cudaGetLastError();

@@ -43,7 +43,7 @@ template <bool LEAKY>
 __global__ void __launch_bounds__(THREADS, 2)
 corr_fwd_tile9_tma_bf16(const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
                         bf16 *__restrict__ out, int C, int H, int W, int tiles_x, int tiles_y, int ntiles, float rc,
-                        float slope) {
+                        float slope, size_t obs) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + NS * STAGE_BYTES);
     uint64_t *empty_bar = full_bar + NS;
@@ -120,7 +120,7 @@ corr_fwd_tile9_tma_bf16(const __grid_constant__ CUtensorMap m1, const __grid_con
 
         const int gy = ty * TH + r, gx = tx * TW + 8 * q;
         if (gy < H && gx < W) {  // W % 8 == 0: an 8-pixel group is entirely inside or outside
-            bf16 *o = out + (((size_t)b * kK + warp * kD) * H + gy) * W + gx;
+            bf16 *o = out + (size_t)b * obs + (((size_t)warp * kD) * H + gy) * W + gx;
             const size_t kstride = (size_t)H * W;
 #pragma unroll
             for (int dx = 0; dx < kD; ++dx, o += kstride) {
@@ -142,7 +142,8 @@ corr_fwd_tile9_tma_bf16(const __grid_constant__ CUtensorMap m1, const __grid_con
 // Returns USF_ERR_UNSUPPORTED when the shape cannot take the TMA path (caller falls back).
 int corr_fwd_bf16_tiled(const void *x1, const void *x2, void *out, int B, int C, int H, int W, unsigned flags,
                         float slope, cudaStream_t stream) {
-    if ((W % 8) != 0 || (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) & 15)) return USF_ERR_UNSUPPORTED;
+    const size_t obs = corr_out_bstride(H, W);
+    if ((W % 8) != 0 || (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out) & 15) || obs % 8 != 0) return USF_ERR_UNSUPPORTED;
     CUtensorMap m1, m2;
     if (!make_nchw_map_bf16(&m1, x1, B, C, H, W, X1E, TH, CK) || !make_nchw_map_bf16(&m2, x2, B, C, H, W, X2E, X2R, CK))
         return USF_ERR_UNSUPPORTED;
@@ -152,10 +153,10 @@ int corr_fwd_bf16_tiled(const void *x1, const void *x2, void *out, int B, int C,
     cudaError_t e;
     if (flags & USF_FLAG_LEAKY_RELU) {
         if ((e = ensure_smem((const void *)corr_fwd_tile9_tma_bf16<true>, SMEM)) != cudaSuccess) return note_launch(e);
-        corr_fwd_tile9_tma_bf16<true><<<grid, THREADS, SMEM, stream>>>(m1, m2, (bf16 *)out, C, H, W, tx, ty, ntiles, rc, slope);
+        corr_fwd_tile9_tma_bf16<true><<<grid, THREADS, SMEM, stream>>>(m1, m2, (bf16 *)out, C, H, W, tx, ty, ntiles, rc, slope, obs);
     } else {
         if ((e = ensure_smem((const void *)corr_fwd_tile9_tma_bf16<false>, SMEM)) != cudaSuccess) return note_launch(e);
-        corr_fwd_tile9_tma_bf16<false><<<grid, THREADS, SMEM, stream>>>(m1, m2, (bf16 *)out, C, H, W, tx, ty, ntiles, rc, slope);
+        corr_fwd_tile9_tma_bf16<false><<<grid, THREADS, SMEM, stream>>>(m1, m2, (bf16 *)out, C, H, W, tx, ty, ntiles, rc, slope, obs);
     }
     return note_launch(cudaGetLastError());
 }

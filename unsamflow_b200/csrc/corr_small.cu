@@ -124,7 +124,7 @@ template <int PX, bool LEAKY, typename T>
 __global__ void __launch_bounds__(kMaxThreads)
 corr_fwd_small(const __grid_constant__ CUtensorMap m1, const __grid_constant__ CUtensorMap m2,
                const T *__restrict__ x1, const T *__restrict__ x2, T *__restrict__ out, int C, int H, int W, int RB,
-               int lgP, int NG, int CK, int S, int tma, float rc, float slope) {
+               int lgP, int NG, int CK, int S, int tma, float rc, float slope, size_t obs) {
     pdl_wait();
     extern __shared__ __align__(1024) float sm[];
     __shared__ uint64_t fill_bar;
@@ -137,7 +137,7 @@ corr_fwd_small(const __grid_constant__ CUtensorMap m1, const __grid_constant__ C
     const bool active = p0 < rows * W;
     const int r = p0 / W, x = p0 - r * W;
     const bool rowok = active && r >= r_lo && r < r_hi;
-    T *optr = out + (((size_t)b * kK + dyi * kD) * H + y0 + r) * W + x;
+    T *optr = out + (size_t)b * obs + (((size_t)dyi * kD) * H + y0 + r) * W + x;
 
     if (r_hi <= r_lo) {  // every displaced row is outside the image: the CTA's outputs are zeros
         if (active) {
@@ -435,11 +435,11 @@ cudaError_t launch_fwd(const T *x1, const T *x2, T *out, int B, int C, int H, in
     if (flags & USF_FLAG_LEAKY_RELU) {
         if ((e = ensure_smem((const void *)corr_fwd_small<PX, true, T>, (int)smem)) != cudaSuccess) return e;
         usf_launch((corr_fwd_small<PX, true, T>), dim3(grid), dim3(P * NG), smem, stream, m1, m2, x1, x2, out, C, H, W, RB, lgP, NG, CK, S,
-                                                                    tma, rc, slope);
+                                                                    tma, rc, slope, corr_out_bstride(H, W));
     } else {
         if ((e = ensure_smem((const void *)corr_fwd_small<PX, false, T>, (int)smem)) != cudaSuccess) return e;
         usf_launch((corr_fwd_small<PX, false, T>), dim3(grid), dim3(P * NG), smem, stream, m1, m2, x1, x2, out, C, H, W, RB, lgP, NG, CK, S,
-                                                                     tma, rc, slope);
+                                                                     tma, rc, slope, corr_out_bstride(H, W));
     }
     return cudaGetLastError();
 }
@@ -478,7 +478,7 @@ bool corr_small_applies(int H, int W) { return (long)H * W <= kSmallMaxHW; }
 template <typename T>
 static int fwd_small(const T *x1, const T *x2, T *out, int B, int C, int H, int W, unsigned flags, float slope,
                      cudaStream_t stream) {
-    if (pairs_ok<T>(W, x1, x2, out)) return note_launch(launch_fwd<2, T>(x1, x2, out, B, C, H, W, flags, slope, stream));
+    if (pairs_ok<T>(W, x1, x2, out) && corr_out_bstride(H, W) % 2 == 0) return note_launch(launch_fwd<2, T>(x1, x2, out, B, C, H, W, flags, slope, stream));
     return note_launch(launch_fwd<1, T>(x1, x2, out, B, C, H, W, flags, slope, stream));
 }
 

@@ -74,17 +74,29 @@ def _flags(leaky=False, reciprocal=False, atomic=False, ws_clean=False):
             | (_lib.FLAG_WARP_BWD_ATOMIC if atomic else 0) | (_lib.FLAG_WORKSPACE_CLEAN if ws_clean else 0))
 
 
+def _is_channel_slice(t, shape, dtype, device):
+    """out= may be a view of 81 consecutive channels of a wider contiguous [B,Ctot,H,W] tensor (the estimator's
+    concat buffer): dense inside an image, a larger batch stride."""
+    B, K, H, W = shape
+    return (isinstance(t, torch.Tensor) and tuple(t.shape) == tuple(shape) and t.dtype == dtype and t.device == device
+            and t.stride()[1:] == (H * W, W, 1) and (B == 1 or t.stride(0) >= K * H * W))
+
+
 def corr_fwd(x1, x2, leaky_slope=None, out=None):
-    """[B,C,H,W] x2 -> [B,81,H,W]; optional fused LeakyReLU(leaky_slope)."""
+    """[B,C,H,W] x2 -> [B,81,H,W]; optional fused LeakyReLU(leaky_slope).  out= is a preallocated contiguous cost
+    volume, or a channel slice `buf[:, k:k+81]` of a wider contiguous tensor (usf_corr_fwd_into)."""
     L = _lib.load()
     x1, x2 = _feat(x1, "x1"), _feat(x2, "x2")
     _same(x1, x2, "x1", "x2")
     if x1.dtype != x2.dtype:
         raise ValueError(f"x1 is {x1.dtype} but x2 is {x2.dtype}")
     B, C, H, W = x1.shape
-    _check_out(out, (B, NUM_DISPLACEMENTS, H, W), x1.dtype, x1.device, "out")
+    shape = (B, NUM_DISPLACEMENTS, H, W)
+    sliced = out is not None and not out.is_contiguous() and _is_channel_slice(out, shape, x1.dtype, x1.device)
+    if not sliced:
+        _check_out(out, shape, x1.dtype, x1.device, "out")
     if x1.numel() == 0:  # empty batch: the reference returns an empty cost volume too
-        return x1.new_empty((B, NUM_DISPLACEMENTS, H, W)) if out is None else out
+        return x1.new_empty(shape) if out is None else out
     if x1.dtype == torch.bfloat16 and B * H * W > BF16_NATIVE_MAX_PIXELS and W % 8 != 0:
         # (W % 8 == 0 takes the native bf16 tiled TMA kernel, csrc/corr_fwd_bf16.cu)
         wide = corr_fwd(x1.float(), x2.float(), leaky_slope)
@@ -93,12 +105,17 @@ def corr_fwd(x1, x2, leaky_slope=None, out=None):
         out.copy_(wide)
         return out
     if out is None:
-        out = torch.empty((B, NUM_DISPLACEMENTS, H, W), dtype=x1.dtype, device=x1.device)
+        out = torch.empty(shape, dtype=x1.dtype, device=x1.device)
+    flags = _flags(leaky=leaky_slope is not None)
     with torch.cuda.device(x1.device):
-        st = L.usf_corr_fwd(x1.data_ptr(), x2.data_ptr(), out.data_ptr(), B, C, H, W, MAX_DISPLACEMENT,
-                            _DTYPES[x1.dtype], _flags(leaky=leaky_slope is not None),
-                            float(leaky_slope or 0.0), _stream(x1))
-    _lib.check(st, "usf_corr_fwd")
+        if sliced:
+            st = L.usf_corr_fwd_into(x1.data_ptr(), x2.data_ptr(), out.data_ptr(), out.stride(0) if B > 1 else
+                                     NUM_DISPLACEMENTS * H * W, B, C, H, W, MAX_DISPLACEMENT, _DTYPES[x1.dtype], flags,
+                                     float(leaky_slope or 0.0), _stream(x1))
+        else:
+            st = L.usf_corr_fwd(x1.data_ptr(), x2.data_ptr(), out.data_ptr(), B, C, H, W, MAX_DISPLACEMENT,
+                                _DTYPES[x1.dtype], flags, float(leaky_slope or 0.0), _stream(x1))
+    _lib.check(st, "usf_corr_fwd_into" if sliced else "usf_corr_fwd")
     return out
 
 

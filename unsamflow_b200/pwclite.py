@@ -26,7 +26,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .correlation import Correlation
+from .correlation import Correlation, cost_concat
 from .segpool import segment_max_pool
 from .warp import flow_warp
 
@@ -134,11 +134,15 @@ def segment_max_pool_torch(feat, seg):
 
 
 class PWCLite(nn.Module):
-    def __init__(self, batch_directions=False, add_mask_corr=False, aggregation_type="concat", num_segments=None):
+    def __init__(self, batch_directions=False, add_mask_corr=False, aggregation_type="concat", num_segments=None,
+                 fuse_cost_concat=False):
         """num_segments: one-hot classes of the segment maps (max id + 1); None reads it from the map on every call
         (a device->host sync, like the reference's F.one_hot); e.g. 256 for uint8 SAM id maps keeps the step sync-free."""
         super().__init__()
         self.num_segments = num_segments
+        # True: the correlation kernels apply the LeakyReLU and write into the estimator's input buffer
+        # (correlation.cost_concat; SURVEY.md 8f rank 1) instead of corr -> LeakyReLU(inplace) -> torch.cat
+        self.fuse_cost_concat = fuse_cost_concat
         self.batch_directions = batch_directions
         self.add_mask_corr = add_mask_corr
         self.aggregation_type = aggregation_type
@@ -184,15 +188,17 @@ class PWCLite(nn.Module):
                 x2_warp = flow_warp(x2, flow)
             else:
                 x2_warp = x2
-            cost = self.leaky(self.corr(x1, x2_warp))
             x1_proj = self.conv_1x1[level](x1)
+            pairs = [(x1, x2_warp)]
             if self.add_mask_corr:
                 m1, m2 = self.mask_features(level, x1, seg1), self.mask_features(level, x2, seg2)
                 # the reference warps with `flow` at every level, the all-zero initial flow included (:355)
-                mask_cost = self.leaky(self.corr(m1, flow_warp(m2, flow)))
-                feat, flow_res = self.flow_estimators(torch.cat([cost, mask_cost, x1_proj, flow], 1))
+                pairs.append((m1, flow_warp(m2, flow)))
+            if self.fuse_cost_concat:
+                est_in = cost_concat(pairs, [x1_proj, flow], 0.1)
             else:
-                feat, flow_res = self.flow_estimators(torch.cat([cost, x1_proj, flow], 1))
+                est_in = torch.cat([self.leaky(self.corr(a, b)) for a, b in pairs] + [x1_proj, flow], 1)
+            feat, flow_res = self.flow_estimators(est_in)
             flow = flow + flow_res
             flow_fine, up_feat = self.context_networks(torch.cat([feat, flow], 1))
             flow = flow + flow_fine
