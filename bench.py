@@ -240,8 +240,9 @@ def time_train_step(args, local, world, barrier):
     backward, clip, Adam; DDP over NCCL when world > 1 (per-GPU batch fixed: weak scaling)."""
     from unsamflow_b200.train_step import TrainStep
     torch.backends.cudnn.benchmark = True  # train.py:19
+    graphed = world == 1  # DDP's bucket hooks are not captured: the multi-GPU step stays eager
     ts = TrainStep(args.batch, args.height, args.width, f"cuda:{local}", seed=42, batch_directions=True,
-                   ddp=world > 1)
+                   ddp=world > 1, cuda_graph=graphed, fuse_cost_concat=True)
     for _ in range(3):
         ts.step()
     barrier()
@@ -252,8 +253,9 @@ def time_train_step(args, local, world, barrier):
     b.record()
     barrier()
     info = {"what": "PWC-Lite kitti_base training step (fwd with_bk + unflow loss + bwd + clip + Adam), synthetic "
-                    f"{args.height}x{args.width} pairs, B={args.batch} per GPU, eager PyTorch around the usf kernels",
-            "batch_directions": True, "loss": float(loss), "ddp": world > 1,
+                    f"{args.height}x{args.width} pairs, B={args.batch} per GPU, PyTorch / cuDNN around the usf kernels, "
+                    f"{'captured in one CUDA graph' if graphed else 'eager (DDP)'}",
+            "batch_directions": True, "fuse_cost_concat": True, "cuda_graph": graphed, "loss": float(loss), "ddp": world > 1,
             "params": ts.model.num_parameters()}
     return a.elapsed_time(b), info
 

@@ -263,3 +263,27 @@ def test_fused_cost_concat_model_equals_the_unfused_one(exact_math):
             if p.grad is not None:
                 worst = max(worst, rel(q.grad, p.grad))
         assert worst <= 1e-5, (mf, worst)
+
+
+def test_cuda_graphed_training_step_follows_the_eager_one(exact_math):
+    """TrainStep(cuda_graph=True): forward + loss + backward + clipping + Adam captured once and replayed.  With a zero
+    learning rate the weights stay put, so every eager iteration and every replay must report the same loss; with the
+    real learning rate the replays must keep updating the parameters (the optimizer step is inside the graph)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from unsamflow_b200.train_step import TrainStep
+    eager = TrainStep(2, 128, 256, "cuda:0", seed=3, batch_directions=True, lr=0.0)
+    graphed = TrainStep(2, 128, 256, "cuda:0", seed=3, batch_directions=True, lr=0.0, cuda_graph=True,
+                        fuse_cost_concat=True)
+    le = [float(eager.step()) for _ in range(2)]
+    lg = [float(graphed.step()) for _ in range(3)]
+    assert graphed.graph is not None
+    assert max(abs(v - le[0]) for v in le + lg) <= 1e-5 * abs(le[0]), (le, lg)
+    live = TrainStep(2, 128, 256, "cuda:0", seed=3, batch_directions=True, cuda_graph=True)
+    live.step()
+    before = [p.detach().clone() for p in live.model.parameters()]
+    live.step()
+    moved = sum(float((p.detach() - q).abs().sum()) for p, q in zip(live.model.parameters(), before))
+    assert moved > 0.0
+    with pytest.raises(ValueError):
+        TrainStep(2, 128, 256, "cuda:0", ddp=True, cuda_graph=True)
