@@ -421,9 +421,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     g2 = capture(lambda: step2.run_concurrent(step2.chains)) if args.streams == 2 else capture(step2.run)
     sets = [(step, gFull), (step2, g2)]
-    host_in = {n: step.t[n].cpu().pin_memory() for n in step.input_names}
-    res_names = step.result_names()
-    host_out = [{n: torch.empty_like(st.t[n], device="cpu").pin_memory() for n in res_names} for st, _ in sets]
+    host_in = step.input_arena.cpu().pin_memory()  # every input of the step, one pinned block (see HotPathStep._pack)
+    host_out = [torch.empty_like(st.result_arena, device="cpu").pin_memory() for st, _ in sets]
     s_in, s_run, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
     in_ready = [torch.cuda.Event() for _ in sets]
     run_done = [torch.cuda.Event() for _ in sets]
@@ -433,8 +432,7 @@ def run_ours(args):
         st, g = sets[i % 2]
         with torch.cuda.stream(s_in):
             s_in.wait_event(run_done[i % 2])          # this buffer set's previous kernels are finished
-            for n, h in host_in.items():
-                st.t[n].copy_(h, non_blocking=True)
+            st.input_arena.copy_(host_in, non_blocking=True)
             in_ready[i % 2].record(s_in)
         with torch.cuda.stream(s_run):
             s_run.wait_event(in_ready[i % 2])
@@ -443,8 +441,7 @@ def run_ours(args):
             run_done[i % 2].record(s_run)
         with torch.cuda.stream(s_out):
             s_out.wait_event(run_done[i % 2])
-            for n, h in host_out[i % 2].items():
-                h.copy_(st.t[n], non_blocking=True)
+            host_out[i % 2].copy_(st.result_arena, non_blocking=True)
             out_done[i % 2].record(s_out)
 
     for i in range(4):
@@ -500,9 +497,10 @@ def run_ours(args):
                          "fp32_peak_tflops": FP32_PEAK_TFLOPS},
             "e2e": {"value": world * args.batch * args.e2e_steps / (e2e_ms / 1e3), "unit": UNIT,
                     "h2d_bytes_per_step": step.input_bytes(),
-                    "d2h_bytes_per_step": sum(h.numel() * h.element_size() for h in host_out[0].values()),
+                    "d2h_bytes_per_step": step.result_bytes(),
                     "steps": args.e2e_steps, "ms_per_step": e2e_ms / args.e2e_steps,
-                    "pipeline": "double-buffered: H2D of step i+1 and D2H of step i-1 overlap the kernels of step i"},
+                    "pipeline": "double-buffered: H2D of step i+1 and D2H of step i-1 overlap the kernels of step i; one pinned "
+                                "block per direction (inputs / results live in one device arena each)"},
             "gpu_launches": step.launches_per_step * args.steps,
             "gpu_launches_note": f"{step.launches_per_step} usf kernels per step, replayed from one CUDA graph in the timed "
                                  f"region ({eager_launches} more issued eagerly through the C ABI by the kernel-alone loop)",
