@@ -45,6 +45,23 @@ for shape in [(8, 128, 8, 26), (8, 96, 16, 52)]:
         bad += 0 if (torch.equal(a, rx) and torch.equal(b, rf)) else 1
     total_bad += bad
     print(f"warp_bwd (fused small-image) {shape}: mismatching runs {bad}/{RUNS}", flush=True)
+# segment max-pooling of the +mf branch: forward (integer atomicMax keys) and backward (fixed-order segment sums)
+from unsamflow_b200 import segpool  # noqa: E402
+for shape, n in [((8, 32, 64, 208), 40), ((8, 32, 16, 52), 256)]:
+    B, C, H, W = shape
+    feat, go = torch.randn(shape, generator=g).cuda(), torch.randn(shape, generator=g).cuda()
+    ids = torch.randint(0, n, (B, H, W), generator=g, dtype=torch.int32).cuda()  # white-noise ids: worst case for the groups
+    ro, ra = (t.clone() for t in segpool.segpool_fwd(feat, ids, n))
+    rg = segpool.segpool_bwd(go, ids, ra, n).clone()
+    bad = 0
+    for i in range(RUNS):
+        if i % 10 == 0:
+            with torch.cuda.stream(side):
+                noise @ noise
+        o, a = segpool.segpool_fwd(feat, ids, n)
+        bad += 0 if (torch.equal(o, ro) and torch.equal(a, ra) and torch.equal(segpool.segpool_bwd(go, ids, a, n), rg)) else 1
+    total_bad += bad
+    print(f"segpool {shape} {n} ids: mismatching runs {bad}/{RUNS}", flush=True)
 torch.cuda.synchronize()
 print("TOTAL mismatching runs:", total_bad)
 sys.exit(1 if total_bad else 0)
