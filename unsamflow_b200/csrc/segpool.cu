@@ -35,6 +35,10 @@ __device__ __forceinline__ int float_key(float f) {  // monotonic: a < b  <=>  k
 __device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
 
 // smem: int cnt[N]; int key[kSpCh][N]; int arg[kSpCh][N]
+// Two sweeps over the image.  Sweep 1: pixel count and in-segment maximum per segment.  Sweep 2: arg-max and the
+// un-pooled output.  Segment maps are piecewise constant, so the 32 pixels of a warp mostly share one segment and
+// would serialise on one shared-memory word: lanes are grouped by segment (match.any) and reduced in registers
+// (redux.sync) first; one lane per group touches shared memory.
 template <typename T, int kSpCh>
 __global__ void __launch_bounds__(kSpBlock)
 segpool_fwd_kernel(const T *__restrict__ feat, const int *__restrict__ seg, T *__restrict__ out,
@@ -42,54 +46,98 @@ segpool_fwd_kernel(const T *__restrict__ feat, const int *__restrict__ seg, T *_
     pdl_wait();
     extern __shared__ int sp_smem[];
     int *cnt = sp_smem, *key = cnt + N, *arg = key + kSpCh * N;
-    const int b = blockIdx.x, c0 = blockIdx.y * kSpCh, tid = threadIdx.x;
+    const int b = blockIdx.x, c0 = blockIdx.y * kSpCh, tid = threadIdx.x, lane = tid & 31;
     const int nc = min(kSpCh, C - c0);
     const int *sg = seg + (size_t)b * HW;
     const T *f = feat + ((size_t)b * C + c0) * HW;
-    for (int i = tid; i < N; i += kSpBlock) cnt[i] = 0;
-    __syncthreads();
-    // (ids outside [0, N) are not segments: such a pixel joins no table and receives 0 / passes no gradient)
-    for (int p = tid; p < HW; p += kSpBlock) {
-        const int s = sg[p];
-        if ((unsigned)s < (unsigned)N) atomicAdd(&cnt[s], 1);
-    }
-    __syncthreads();
     const int kneg = float_key(-INFINITY);
+    for (int i = tid; i < N; i += kSpBlock) cnt[i] = 0;
     for (int i = tid; i < kSpCh * N; i += kSpBlock) {
-        key[i] = cnt[i % N] == HW ? kneg : 0;  // 0 = key(0.0f): the zeros of the pixels outside the segment
+        key[i] = kneg;
         arg[i] = 0x7fffffff;
     }
     __syncthreads();
-    for (int p = tid; p < HW; p += kSpBlock) {
-        const int s = sg[p];
-        if ((unsigned)s >= (unsigned)N) continue;
+    // whole warps (the votes need every lane), four iterations' loads in flight at once: the sweeps are bound by the
+    // latency of one dependent load per iteration otherwise
+    constexpr int U = 4;
+    const int sweep = (HW + U * kSpBlock - 1) / (U * kSpBlock) * (U * kSpBlock);
+    for (int p0 = tid; p0 < sweep; p0 += U * kSpBlock) {
+        int sv[U], kv[U][kSpCh];
 #pragma unroll
-        for (int k = 0; k < kSpCh; ++k)
-            if (k < nc) atomicMax(&key[k * N + s], float_key(ldf(f + (size_t)k * HW + p)));
-    }
-    __syncthreads();
-    if (argmax != nullptr) {
-        for (int p = tid; p < HW; p += kSpBlock) {
-            const int s = sg[p];
-            if ((unsigned)s >= (unsigned)N) continue;
+        for (int u = 0; u < U; ++u) {
+            const int p = p0 + u * kSpBlock;
+            // (ids outside [0, N) are not segments: such a pixel joins no table and receives 0 / passes no gradient)
+            int s = p < HW ? sg[p] : -1;
+            if ((unsigned)s >= (unsigned)N) s = -1;
+            sv[u] = s;
 #pragma unroll
             for (int k = 0; k < kSpCh; ++k)
-                if (k < nc && float_key(ldf(f + (size_t)k * HW + p)) == key[k * N + s]) atomicMin(&arg[k * N + s], p);
+                kv[u][k] = (p < HW && k < nc) ? float_key(ldf(f + (size_t)k * HW + p)) : kneg;
         }
-        __syncthreads();
-        // -1: the clamp at zero won (or tied): no pixel receives the gradient
-        for (int i = tid; i < nc * N; i += kSpBlock) {
-            const int a = arg[i];
-            argmax[((size_t)b * C + c0) * N + i] = a == 0x7fffffff ? -1 : a;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int s = sv[u];
+            // (a redux.sync over a PARTIAL mask is emulated by a loop: only the all-lanes-equal case, one instruction,
+            // is worth taking; mixed warps fall back to one atomic per lane)
+            if (__all_sync(0xffffffffu, s == __shfl_sync(0xffffffffu, s, 0))) {
+                if (s < 0) continue;  // uniform
+                if (lane == 0) atomicAdd(&cnt[s], 32);
+#pragma unroll
+                for (int k = 0; k < kSpCh; ++k) {
+                    const int best = __reduce_max_sync(0xffffffffu, kv[u][k]);
+                    if (lane == 0 && k < nc) atomicMax(&key[k * N + s], best);
+                }
+            } else if (s >= 0) {
+                atomicAdd(&cnt[s], 1);
+#pragma unroll
+                for (int k = 0; k < kSpCh; ++k)
+                    if (k < nc) atomicMax(&key[k * N + s], kv[u][k]);
+            }
         }
     }
+    __syncthreads();
     T *o = out + ((size_t)b * C + c0) * HW;
-    for (int p = tid; p < HW; p += kSpBlock) {
-        const int s = sg[p];
-        const bool in = (unsigned)s < (unsigned)N;
+    for (int p0 = tid; p0 < sweep; p0 += U * kSpBlock) {
+        int sv[U], kv[U][kSpCh];
 #pragma unroll
-        for (int k = 0; k < kSpCh; ++k)
-            if (k < nc) stf(o + (size_t)k * HW + p, in ? key_float(key[k * N + s]) : 0.f);
+        for (int u = 0; u < U; ++u) {
+            const int p = p0 + u * kSpBlock;
+            int s = p < HW ? sg[p] : -1;
+            if ((unsigned)s >= (unsigned)N) s = -1;
+            sv[u] = s;
+#pragma unroll
+            for (int k = 0; k < kSpCh; ++k)
+                kv[u][k] = (argmax != nullptr && p < HW && k < nc) ? float_key(ldf(f + (size_t)k * HW + p)) : kneg;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = p0 + u * kSpBlock, s = sv[u];
+            const bool uni = __all_sync(0xffffffffu, s == __shfl_sync(0xffffffffu, s, 0));
+            const bool whole = s >= 0 && cnt[s] == HW;  // the segment covers the image: no zero from outside competes
+#pragma unroll
+            for (int k = 0; k < kSpCh; ++k) {
+                const int top = (s >= 0 && k < nc) ? key[k * N + s] : 0;
+                if (argmax != nullptr) {
+                    const int mine = (s >= 0 && k < nc && kv[u][k] == top) ? p : 0x7fffffff;
+                    if (uni) {
+                        const int first = __reduce_min_sync(0xffffffffu, mine);
+                        if (lane == 0 && first != 0x7fffffff) atomicMin(&arg[k * N + s], first);
+                    } else if (mine != 0x7fffffff) {
+                        atomicMin(&arg[k * N + s], mine);
+                    }
+                }
+                // key(0.0f) == 0: the clamp at zero is a max of integer keys
+                if (p < HW && k < nc) stf(o + (size_t)k * HW + p, s >= 0 ? key_float(whole ? top : max(top, 0)) : 0.f);
+            }
+        }
+    }
+    if (argmax == nullptr) return;
+    __syncthreads();
+    // -1: the clamp at zero won or tied (no pixel receives the gradient), or the class is empty
+    for (int i = tid; i < nc * N; i += kSpBlock) {
+        const int n = i % N;
+        const bool taken = cnt[n] > 0 && (cnt[n] == HW || key[i] > 0);
+        argmax[((size_t)b * C + c0) * N + i] = taken ? arg[i] : -1;
     }
 }
 
@@ -109,52 +157,63 @@ segpool_bwd_kernel(const T *__restrict__ gout, const int *__restrict__ seg, cons
     __syncthreads();
     // warp `wid` owns pixels [lo, hi): a fixed partition, swept in increasing order
     const int per = (HW + kSpWarps - 1) / kSpWarps, lo = wid * per, hi = min(HW, lo + per);
-    for (int base = lo; base < hi; base += 32) {
-        const int p = base + lane;
-        int s = p < hi ? sg[p] : -1;
-        if ((unsigned)s >= (unsigned)N) s = -1;
-        const bool on = s >= 0;
-        float v[kSpCh];
+    constexpr int U = 4;  // four groups of 32 pixels loaded together, then reduced one after the other (in order)
+    for (int base0 = lo; base0 < hi; base0 += 32 * U) {
+        int sv[U];
+        float vv[U][kSpCh];
 #pragma unroll
-        for (int k = 0; k < kSpCh; ++k) v[k] = (on && k < nc) ? ldf(g + (size_t)k * HW + p) : 0.f;
-        const unsigned grp = __match_any_sync(0xffffffffu, s);
-        const int leader = __ffs(grp) - 1;
-        // sum the lanes of each group in lane order: every lane walks its own group's members (the lanes of a group
-        // walk the same list, so they compute the same sum); warps are usually inside ONE segment, one group of 32
-        float sum[kSpCh];
+        for (int u = 0; u < U; ++u) {
+            const int p = base0 + 32 * u + lane;
+            int s = p < hi ? sg[p] : -1;
+            if ((unsigned)s >= (unsigned)N) s = -1;
+            sv[u] = s;
 #pragma unroll
-        for (int k = 0; k < kSpCh; ++k) sum[k] = 0.f;
-        if (grp == 0xffffffffu) {
-            // the usual case -- all 32 pixels in one segment (every lane sees the full mask, so the branch is uniform):
-            // a butterfly, whose order is fixed too
+            for (int k = 0; k < kSpCh; ++k) vv[u][k] = (s >= 0 && k < nc) ? ldf(g + (size_t)k * HW + p) : 0.f;
+        }
 #pragma unroll
-            for (int k = 0; k < kSpCh; ++k) {
-                float t = v[k];
+        for (int u = 0; u < U; ++u) {
+            if (base0 + 32 * u >= hi) break;  // warp-uniform
+            const int s = sv[u];
+            const bool on = s >= 0;
+            const unsigned grp = __match_any_sync(0xffffffffu, s);
+            const int leader = __ffs(grp) - 1;
+            // sum the lanes of each group in lane order: every lane walks its own group's members (the lanes of a
+            // group walk the same list, so they compute the same sum); warps are usually inside ONE segment
+            float sum[kSpCh];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-                sum[k] = t;
-            }
-        } else {
-            // uniform trip count: the size of the largest group in the warp
-            int most = __popc(grp);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) most = max(most, __shfl_xor_sync(0xffffffffu, most, o));
-            unsigned rest = grp;
-            for (int it = 0; it < most; ++it) {
-                const int srcl = rest ? __ffs(rest) - 1 : lane;
+            for (int k = 0; k < kSpCh; ++k) sum[k] = 0.f;
+            if (grp == 0xffffffffu) {
+                // all 32 pixels in one segment (every lane sees the full mask, so the branch is uniform): a butterfly,
+                // whose order is fixed too
 #pragma unroll
                 for (int k = 0; k < kSpCh; ++k) {
-                    const float t = __shfl_sync(0xffffffffu, v[k], srcl);
-                    if (rest) sum[k] += t;
-                }
-                rest &= rest - 1;
-            }
-        }
-        if (on && lane == leader) {
+                    float t = vv[u][k];
 #pragma unroll
-            for (int k = 0; k < kSpCh; ++k) mine[k * N + s] += sum[k];  // single writer per (warp, segment) at a time
+                    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                    sum[k] = t;
+                }
+            } else {
+                // uniform trip count: the size of the largest group in the warp
+                int most = __popc(grp);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) most = max(most, __shfl_xor_sync(0xffffffffu, most, o));
+                unsigned rest = grp;
+                for (int it = 0; it < most; ++it) {
+                    const int srcl = rest ? __ffs(rest) - 1 : lane;
+#pragma unroll
+                    for (int k = 0; k < kSpCh; ++k) {
+                        const float t = __shfl_sync(0xffffffffu, vv[u][k], srcl);
+                        if (rest) sum[k] += t;
+                    }
+                    rest &= rest - 1;
+                }
+            }
+            if (on && lane == leader) {
+#pragma unroll
+                for (int k = 0; k < kSpCh; ++k) mine[k * N + s] += sum[k];  // single writer per (warp, segment) at a time
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
     __syncthreads();
     // tables of the 8 warps added in warp order, into warp 0's table
@@ -167,6 +226,7 @@ segpool_bwd_kernel(const T *__restrict__ gout, const int *__restrict__ seg, cons
     __syncthreads();
     const int *am = argmax + ((size_t)b * C + c0) * N;
     T *o = gfeat + ((size_t)b * C + c0) * HW;
+#pragma unroll 4
     for (int p = tid; p < HW; p += kSpBlock) {
         const int s = sg[p];
         const bool in = (unsigned)s < (unsigned)N;
