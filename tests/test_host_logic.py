@@ -83,6 +83,31 @@ def test_preallocated_buffers_are_validated():
         ops._check_ws(torch.empty(128, dtype=torch.uint8)[1:], 64, dev)
 
 
+def test_round2_callers_fail_loudly_on_cpu_and_validate_arguments():
+    """segment_max_pool (models/pwclite.py:317-340) and cost_concat (:307-308, 364-366) have no CPU path either."""
+    from unsamflow_b200 import segment_max_pool
+    from unsamflow_b200.correlation import cost_concat
+    feat, seg = torch.zeros(1, 4, 6, 8), torch.zeros(1, 1, 6, 8)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        segment_max_pool(feat, seg)
+    with pytest.raises(ValueError):
+        segment_max_pool(torch.zeros(4, 6, 8), seg)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cost_concat([(feat, feat)], [torch.zeros(1, 2, 6, 8)])
+    # signature of the reference-facing entry: segment_max_pool(feat, seg, num_segments=None)
+    params = list(inspect.signature(segment_max_pool).parameters.values())
+    assert [(p.name, p.default) for p in params] == [("feat", inspect.Parameter.empty), ("seg", inspect.Parameter.empty),
+                                                     ("num_segments", None)]
+    # out= of corr_fwd may be a channel slice of a wider contiguous tensor, nothing else that is non-contiguous
+    from unsamflow_b200 import ops
+    buf = torch.empty(2, 115, 6, 8)
+    dev = buf.device
+    assert ops._is_channel_slice(buf[:, 3:84], (2, 81, 6, 8), torch.float32, dev)
+    assert not ops._is_channel_slice(buf[:, 3:84, :, ::2], (2, 81, 6, 4), torch.float32, dev)
+    assert not ops._is_channel_slice(buf[:, 3:84].transpose(2, 3), (2, 81, 8, 6), torch.float32, dev)
+    assert not ops._is_channel_slice(buf[:, 3:84], (2, 81, 6, 8), torch.bfloat16, dev)
+
+
 def test_product_never_imports_the_oracle():
     import os
     import re
