@@ -566,6 +566,9 @@ const int kWarpSmallMaxHW = [] {
 }();
 
 int pick_ns(int C, int N) {
+    // USF_WARP_NS=<power of two>: force the number of channel slices (tuning runs)
+    static const int forced = [] { const char *e = getenv("USF_WARP_NS"); return e ? atoi(e) : 0; }();
+    if (forced >= 1 && forced <= 32 && (forced & (forced - 1)) == 0 && C >= forced) return forced;
     // at least two slices once there are 16 channels: one thread walking 32 channels of a level that does not
     // fit in L2 (64x32x64x208) ran the gather at 10 % of DRAM bandwidth (ncu), two slices at twice that
     int ns = C >= 16 ? 2 : 1;
