@@ -43,6 +43,10 @@ def test_ours_json_contract_on_gpu():
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 1000
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0 < r["frac"] < 1.5
+    # the dominant kernel is timed twice: alone inside the step, and in place inside the step's CUDA graph
+    assert r["us_per_launch"] > 0 and r["us_per_launch_in_place"] >= 0.9 * r["us_per_launch"] and r["timing"]
+    assert abs(r["achieved"] - r["alg_bytes_per_launch"] / r["us_per_launch"] / 1e3) < 1e-6 * r["achieved"]
+    assert "one CUDA graph" in d["config"]["step"]
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"]
     assert d["gpu_launches"] >= 5 * 60                      # >= 60 of our kernels per step
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
