@@ -97,6 +97,88 @@ warp_fwd_kernel(const T *__restrict__ x, const float *__restrict__ flow, T *__re
 }
 
 // ---------------------------------------------------------------------------------------------
+// The loss-side calls (losses/flow_loss.py:130-131: a 3-channel image, gradient wrt the flow only) are ISSUE-bound,
+// not memory-bound (69 % issue-active with DRAM at 22-26 %, ncu round 2), and 40 % of their instructions were 64-bit
+// address arithmetic.  These two kernels are the C = 3 forms of warp_fwd_kernel / warp_bwd_kernel<.., 0> with
+//   * 32-bit element offsets (api.cu bounds every tensor of a call to 2^31-1 elements): one IMAD.WIDE per row
+//     pointer instead of 64-bit multiply chains;
+//   * the (image, pixel) split of the NEXT pixel, needed for the flow prefetch, carried into the next iteration
+//     instead of being recomputed.
+// Same arithmetic, bit-identical results.  (The multi-channel kernels keep their pointer-bump loops: there the
+// offsets cost an IMAD.WIDE per load and a few registers, and the same change made them 15-30 % slower.)
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(kBlock, 6)
+warp_rgb_kernel(const T *__restrict__ x, const float *__restrict__ flow, const T *__restrict__ gout, T *__restrict__ out,
+                float *__restrict__ gflow, int N, int H, int W, int border, int rcp, FastDiv dHW, FastDiv dW, AxisK kx,
+                AxisK ky) {
+    pdl_wait();
+    constexpr int C = 3;
+    const int HW = H * W, stride = gridDim.x * kBlock;
+    int p = blockIdx.x * kBlock + threadIdx.x;
+    float u = 0.f, v = 0.f;
+    int b = 0, rem = 0;
+    if (p < N) {
+        b = dHW.div(p);
+        rem = p - b * HW;
+        const int fo = b * 2 * HW + rem;
+        u = __ldg(flow + fo);
+        v = __ldg(flow + fo + HW);
+    }
+    while (p < N) {
+        const int y = dW.div(rem), xo = rem - y * W;
+        const int pn = p + stride;
+        float un = 0.f, vn = 0.f;
+        int bn = 0, remn = 0;
+        if (pn < N) {
+            bn = dHW.div(pn);
+            remn = pn - bn * HW;
+            const int fo = bn * 2 * HW + remn;
+            un = __ldg(flow + fo);
+            vn = __ldg(flow + fo + HW);
+        }
+        const Taps t = make_taps_k((float)y, (float)xo, u, v, H, W, kx, ky, border, rcp);
+        const int plane = b * C * HW;
+        int i0 = plane + t.o_nw, io = plane + rem;
+        if (!BWD) {
+            const float nw = t.ex * t.ey, ne = t.wx * t.ey, sw = t.ex * t.wy, se = t.wx * t.wy;
+#pragma unroll
+            for (int c = 0; c < C; ++c, i0 += HW, io += HW) {
+                const T *p0 = x + i0, *p1 = x + (i0 + W);
+                float acc = (t.k_nw ? ldf(p0) : 0.f) * nw;
+                acc = fmaf(t.k_ne ? ldf(p0 + 1) : 0.f, ne, acc);
+                acc = fmaf(t.k_sw ? ldf(p1) : 0.f, sw, acc);
+                acc = fmaf(t.k_se ? ldf(p1 + 1) : 0.f, se, acc);
+                stf(out + io, acc);
+            }
+        } else {
+            float gix = 0.f, giy = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c, i0 += HW, io += HW) {
+                const T *p0 = x + i0, *p1 = x + (i0 + W);
+                const float go = ldf(gout + io);
+                const float vnw = t.k_nw ? ldf(p0) : 0.f, vne = t.k_ne ? ldf(p0 + 1) : 0.f;
+                const float vsw = t.k_sw ? ldf(p1) : 0.f, vse = t.k_se ? ldf(p1 + 1) : 0.f;
+                gix = fmaf(go, fmaf(t.ey, vne - vnw, t.wy * (vse - vsw)), gix);
+                giy = fmaf(go, fmaf(t.ex, vsw - vnw, t.wx * (vse - vne)), giy);
+            }
+            // grid_sampler backward: ggrid = mult * gi; norm_grid backward: (g / (size-1)) * 2
+            const float gxn = __fmul_rn(t.mx, gix), gyn = __fmul_rn(t.my, giy);
+            const float dfx = rcp ? __fmul_rn(gxn, kx.rcp) : div_by_size(gxn, kx);
+            const float dfy = rcp ? __fmul_rn(gyn, ky.rcp) : div_by_size(gyn, ky);
+            const int fo = b * 2 * HW + rem;
+            gflow[fo] = __fmul_rn(dfx, 2.0f);
+            gflow[fo + HW] = __fmul_rn(dfy, 2.0f);
+        }
+        p = pn;
+        b = bn;
+        rem = remn;
+        u = un;
+        v = vn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Workspace of the atomic-free g_x path, N = B*H*W target pixels:
 //   int   cnt[N]            taps received per target
 //   int   ovf_n[4]          [0] number of overflow taps, [1] CTAs of the gather that have finished
@@ -616,9 +698,10 @@ static int warp_fwd_t(const T *x, const float *flow, T *out, int B, int C, int H
         usf_launch((warp_fwd_kernel<NS, T>), dim3(blocks < res ? blocks : res), dim3(kBlock), 0, stream, x, flow, out, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W), make_axis(W), make_axis(H)); \
     }
     if (ns == 1 && C == 3) {  // loss-side warp of an RGB image
-        const int res = resident_ctas((const void *)warp_fwd_kernel<1, T, 3>);
-        usf_launch((warp_fwd_kernel<1, T, 3>), dim3(blocks < res ? blocks : res), dim3(kBlock), 0, stream, 
-            x, flow, out, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W), make_axis(W), make_axis(H));
+        const int res = resident_ctas((const void *)warp_rgb_kernel<T, false>);
+        usf_launch((warp_rgb_kernel<T, false>), dim3(blocks < res ? blocks : res), dim3(kBlock), 0, stream, x, flow,
+                   (const T *)nullptr, out, (float *)nullptr, N, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W),
+                   make_axis(W), make_axis(H));
         return note_launch(cudaGetLastError());
     }
     switch (ns) {
@@ -664,9 +747,10 @@ static int warp_bwd_t(const T *x, const float *flow, const T *gout, T *gx, float
     Workspace ws = {};
     if (gx == nullptr) {
         if (ns == 1 && C == 3) {  // loss-side warp of an RGB image: gradient wrt the flow only
-            const int res = resident_ctas((const void *)warp_bwd_kernel<1, 0, T, 3>);
-            usf_launch((warp_bwd_kernel<1, 0, T, 3>), dim3(blocks < res ? blocks : res), dim3(kBlock), 0, stream, 
-                x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W), make_axis(W), make_axis(H));
+            const int res = resident_ctas((const void *)warp_rgb_kernel<T, true>);
+            usf_launch((warp_rgb_kernel<T, true>), dim3(blocks < res ? blocks : res), dim3(kBlock), 0, stream, x, flow, gout,
+                       (T *)nullptr, gflow, N, H, W, border, rcp, make_fastdiv(H * W), make_fastdiv(W), make_axis(W),
+                       make_axis(H));
             return note_launch(cudaGetLastError());
         }
         return note_launch(launch_bwd<0, T>(ns, blocks, x, flow, gout, gx, gflow, ws, N, C, H, W, border, rcp, stream));
